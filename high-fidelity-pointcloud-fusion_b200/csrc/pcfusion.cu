@@ -1,0 +1,904 @@
+// pcfusion.cu -- context management and the C ABI of libpcfusion.so (see include/pcfusion.h).
+// The host side here replaces the reference's L2 pipeline (three std::threads + two mutex-protected deques,
+// node.cpp:130-143,218-325) with pinned staging + two CUDA streams, and OccupancyGrid's containers
+// (OG.hpp:99-136) with the flat HBM arrays described at the top of pcf_kernels.cuh.
+// There is deliberately no CPU fallback: without a CUDA device pcf_create fails with PCF_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pcfusion.h"
+#include "pcf_kernels.cuh"
+
+using namespace pcf;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {   // grow-only device allocation
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+constexpr int kRing = 4;           // staging slots for host frames
+constexpr uint32_t kMaxChunks = 1u << 21;   // slot index must fit 32 bits: 2^21 chunks * 2048
+
+}  // namespace
+
+struct pcf_ctx {
+    pcf_config cfg{};
+    GridParams g{};
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    std::string err;
+    bool started = false;
+
+    // persistent grid state
+    uint32_t* first_frame = nullptr;
+    uint32_t* holder = nullptr;           // lazily allocated
+    uint32_t* nrm_bits = nullptr;
+    uint32_t* occ_bits = nullptr;
+    uint32_t* occ_rank = nullptr;
+    uint64_t n_words = 0;
+    bool occ_dirty = true;
+    uint32_t n_vox = 0;                   // occupied cells at the last bitmap build
+    float4* vp_table = nullptr;
+    // point log
+    float4* log = nullptr;
+    uint32_t* chunk_count = nullptr;
+    uint32_t cap_chunks = 0, n_chunks = 0;
+    // normals (append-only records)
+    DevBuf n_cell, n_nrm, n_mark;
+    uint32_t n_normals = 0;
+    std::vector<uint32_t> marks;                       // log slot cursor at each update pass
+    std::vector<std::pair<uint32_t, uint32_t>> pending_holder;   // [begin,end) normal records per pass not yet registered
+    int64_t last_frame_idx = -1;
+
+    // staging for host frames
+    float* stage[kRing] = {};
+    size_t stage_cap[kRing] = {};
+    cudaEvent_t ev_copied[kRing] = {}, ev_free[kRing] = {};
+    int ring_pos = 0;
+    FrameDesc* desc_dev = nullptr;        // batch descriptors
+    FrameDesc* desc_host = nullptr;       // pinned
+    uint32_t desc_cap = 0;
+    cudaEvent_t ev_desc = nullptr;
+
+    // scratch
+    DevBuf scan1, scan2, tmpA, tmpB, tmpC, tmpD, hist, keysA, keysB, valsA, valsB, sorted, uv_cell, uv_off, nidx,
+        sc_a, sc_b, sc_c, flags, slots, cand, res_dev, total_dev;
+    uint32_t* total_host = nullptr;       // pinned, 4 words
+    // host results (pinned)
+    void* res_host = nullptr;
+    size_t res_host_cap = 0;
+    void* st_host = nullptr;
+    size_t st_host_cap = 0;
+
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
+    float t_update = 0, t_extract_dev = 0, t_extract_d2h = 0;
+    pcf_stats stats{};
+    // derived state valid after prepare_sorted()
+    uint64_t n_points = 0;
+    bool sorted_valid = false;
+};
+
+namespace {
+
+int fail(pcf_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(c, PCF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define LAUNCH(c, kernel, grid, block, ...)                      \
+    do {                                                         \
+        kernel<<<(grid), (block), 0, (c)->stream>>>(__VA_ARGS__); \
+        (c)->stats.kernel_launches++;                            \
+    } while (0)
+
+inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+int reserve(pcf_ctx* c, DevBuf& b, size_t bytes, bool keep = false) {
+    if (bytes <= b.cap) return PCF_OK;
+    size_t want = keep ? std::max(bytes, b.cap * 2) : bytes + bytes / 8;
+    void* np = nullptr;
+    CU(cudaMalloc(&np, want));
+    if (keep && b.p && b.cap) {
+        CU(cudaMemcpyAsync(np, b.p, b.cap, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    if (b.p) {
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaFree(b.p));
+    }
+    b.p = np;
+    b.cap = want;
+    return PCF_OK;
+}
+
+float thr_hi(double v) {   // smallest float f with double(f) >= v  :  (double)x >= v  <=>  x >= f
+    float f = (float)v;
+    if ((double)f < v) f = std::nextafterf(f, INFINITY);
+    return f;
+}
+float thr_lo(double v) {   // largest float f with double(f) <= v   :  (double)x <= v  <=>  x <= f
+    float f = (float)v;
+    if ((double)f > v) f = std::nextafterf(f, -INFINITY);
+    return f;
+}
+
+int build_grid_params(pcf_ctx* c) {
+    const pcf_config& cfg = c->cfg;
+    GridParams& g = c->g;
+    if (cfg.k_neighbourhood != 2) return fail(c, PCF_ERR_INVALID, "only k_neighbourhood=2 is supported (OG.hpp:334 hard-codes 125 probes)");
+    if (cfg.walk_k < 0 || cfg.walk_k > 3) return fail(c, PCF_ERR_INVALID, "walk_k must be in [0,3]");
+    for (int a = 0; a < 3; a++) {
+        double lo = cfg.box[2 * a], hi = cfg.box[2 * a + 1];
+        if (!(cfg.res[a] > 0.f) || !(hi > lo)) return fail(c, PCF_ERR_INVALID, "bad box/resolution on axis %d", a);
+        g.min[a] = lo;
+        g.res[a] = (double)cfg.res[a];
+        g.inv_res[a] = 1.0 / g.res[a];
+        g.half_res[a] = g.res[a] / 2.0;
+        g.lo[a] = thr_lo(lo);
+        g.hi[a] = thr_hi(hi);
+        double d = (hi - lo) / g.res[a];
+        if (d >= 1048575.0) return fail(c, PCF_ERR_INVALID, "grid dimension exceeds the 20-bit hash field (OG.hpp:151-165)");
+        g.dim[a] = (int)d;                       // truncation, OG.hpp:623-625
+        g.n1[a] = (uint32_t)g.dim[a] + 1;
+    }
+    g.cells = (uint64_t)g.n1[0] * g.n1[1] * g.n1[2];
+    if (g.cells >= 0xFFFFFFFFull) return fail(c, PCF_ERR_INVALID, "grid has %llu cells; the cell index is 32 bit", (unsigned long long)g.cells);
+    g.clip_lo = thr_lo(cfg.clip_zmin);
+    g.clip_hi = thr_hi(cfg.clip_zmax);
+    g.walk_k = cfg.walk_k;
+    for (int s = 0; s < 7; s++) g.walk_step[s] = 0.f;
+    for (int i = -cfg.walk_k; i <= cfg.walk_k; i++) g.walk_step[i + cfg.walk_k] = (float)((double)i * g.res[0]);   // OG.hpp:405 uses xres_
+    g.min_neighbours = cfg.min_neighbours;
+    g.ball_radius_f = (float)cfg.ball_radius;
+    g.cylinder_radius = cfg.cylinder_radius;
+    return PCF_OK;
+}
+
+// ---- device-wide exclusive scan (in == out allowed); optional total to total_dev[slot] --------------------
+int scan_u32(pcf_ctx* c, const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* total_dev) {
+    if (n == 0) {
+        if (total_dev) CU(cudaMemsetAsync(total_dev, 0, 4, c->stream));
+        return PCF_OK;
+    }
+    uint32_t nb1 = div_up(n, kChunk);
+    if (nb1 == 1) {
+        LAUNCH(c, k_scan_tiles, 1, kBlock, in, out, n, (const uint32_t*)nullptr, total_dev);
+        return PCF_OK;
+    }
+    int rc = reserve(c, c->scan1, (size_t)nb1 * 4);
+    if (rc) return rc;
+    uint32_t* s1 = (uint32_t*)c->scan1.p;
+    LAUNCH(c, k_block_sums, nb1, kBlock, in, n, s1);
+    uint32_t nb2 = div_up(nb1, kChunk);
+    if (nb2 == 1) {
+        LAUNCH(c, k_scan_tiles, 1, kBlock, s1, s1, (uint64_t)nb1, (const uint32_t*)nullptr, (uint32_t*)nullptr);
+    } else {
+        rc = reserve(c, c->scan2, (size_t)nb2 * 4);
+        if (rc) return rc;
+        uint32_t* s2 = (uint32_t*)c->scan2.p;
+        LAUNCH(c, k_block_sums, nb2, kBlock, s1, (uint64_t)nb1, s2);
+        LAUNCH(c, k_scan_tiles, 1, kBlock, s2, s2, (uint64_t)nb2, (const uint32_t*)nullptr, (uint32_t*)nullptr);   // nb2 <= 2048
+        LAUNCH(c, k_scan_tiles, nb2, kBlock, s1, s1, (uint64_t)nb1, s2, (uint32_t*)nullptr);
+    }
+    LAUNCH(c, k_scan_tiles, nb1, kBlock, in, out, n, s1, total_dev);
+    return PCF_OK;
+}
+
+int read_total(pcf_ctx* c, const uint32_t* total_dev, uint32_t* out) {
+    CU(cudaMemcpyAsync(c->total_host, total_dev, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += 4;
+    *out = c->total_host[0];
+    return PCF_OK;
+}
+
+int ensure_log(pcf_ctx* c, uint32_t need_chunks) {
+    if (need_chunks <= c->cap_chunks) return PCF_OK;
+    if (need_chunks > kMaxChunks) return fail(c, PCF_ERR_CAPACITY, "point log limit reached (%u chunks of %d input points)", kMaxChunks, kChunk);
+    uint32_t cap = std::max<uint32_t>(need_chunks, std::min<uint64_t>((uint64_t)c->cap_chunks * 2, kMaxChunks));
+    float4* nl = nullptr;
+    uint32_t* nc = nullptr;
+    CU(cudaMalloc(&nl, (size_t)cap * kChunk * sizeof(float4)));
+    CU(cudaMalloc(&nc, (size_t)cap * 4));
+    if (c->n_chunks) {
+        CU(cudaMemcpyAsync(nl, c->log, (size_t)c->n_chunks * kChunk * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(nc, c->chunk_count, (size_t)c->n_chunks * 4, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->log) CU(cudaFree(c->log));
+    if (c->chunk_count) CU(cudaFree(c->chunk_count));
+    c->log = nl;
+    c->chunk_count = nc;
+    c->cap_chunks = cap;
+    return PCF_OK;
+}
+
+// occupancy bitmap + rank from the dense grid (shared by update and extraction)
+int build_occupancy(pcf_ctx* c) {
+    if (!c->occ_dirty) return PCF_OK;
+    int rc = reserve(c, c->tmpA, (size_t)c->n_words * 4);
+    if (rc) return rc;
+    uint32_t* pop = (uint32_t*)c->tmpA.p;
+    uint32_t blocks = std::min<uint32_t>(div_up(c->n_words * 32, kBlock), 148 * 16);
+    LAUNCH(c, k_cells_to_bits, blocks, kBlock, c->first_frame, c->g.cells, c->occ_bits, pop, c->n_words);
+    uint32_t* tot = (uint32_t*)c->total_dev.p;
+    rc = scan_u32(c, pop, c->occ_rank, c->n_words, tot);
+    if (rc) return rc;
+    rc = read_total(c, tot, &c->n_vox);
+    if (rc) return rc;
+    c->occ_dirty = false;
+    return PCF_OK;
+}
+
+// holder registration of passes that have not been followed by a frame yet (OG.hpp:443-449)
+int flush_holders(pcf_ctx* c) {
+    if (c->pending_holder.empty()) return PCF_OK;
+    if (!c->holder) {
+        CU(cudaMalloc(&c->holder, c->g.cells * 4));
+        CU(cudaMemsetAsync(c->holder, 0, c->g.cells * 4, c->stream));
+    }
+    // occupancy is unchanged since those passes (no frame was pushed in between), so occ_bits is current
+    for (auto& pr : c->pending_holder) {
+        uint32_t n = pr.second - pr.first;
+        if (!n) continue;
+        LAUNCH(c, k_holder<true>, div_up(n, kBlock), kBlock, (const uint32_t*)c->n_cell.p, (const float4*)c->n_nrm.p, pr.first,
+               pr.second, c->g, c->occ_bits, c->holder);
+        LAUNCH(c, k_holder<false>, div_up(n, kBlock), kBlock, (const uint32_t*)c->n_cell.p, (const float4*)c->n_nrm.p, pr.first,
+               pr.second, c->g, c->occ_bits, c->holder);
+    }
+    c->pending_holder.clear();
+    return PCF_OK;
+}
+
+template <bool BATCH>
+int launch_ingest(pcf_ctx* c, uint32_t stride, dim3 grid, const FrameDesc* descs, const FrameDesc& single) {
+    if (stride == 4)
+        LAUNCH(c, (k_ingest<4, BATCH>), grid, kBlock, descs, single, stride, c->g, c->first_frame, c->log, c->chunk_count, c->vp_table);
+    else if (stride == 3)
+        LAUNCH(c, (k_ingest<3, BATCH>), grid, kBlock, descs, single, stride, c->g, c->first_frame, c->log, c->chunk_count, c->vp_table);
+    else
+        LAUNCH(c, (k_ingest<0, BATCH>), grid, kBlock, descs, single, stride, c->g, c->first_frame, c->log, c->chunk_count, c->vp_table);
+    CU(cudaGetLastError());
+    return PCF_OK;
+}
+
+int check_frame_idx(pcf_ctx* c, uint32_t first, uint32_t count) {
+    if ((int64_t)first <= c->last_frame_idx) return fail(c, PCF_ERR_INVALID, "frame_idx %u does not increase (last %lld)", first, (long long)c->last_frame_idx);
+    if ((uint64_t)first + count > c->cfg.max_frames) return fail(c, PCF_ERR_CAPACITY, "frame_idx %u exceeds max_frames %u", first + count - 1, c->cfg.max_frames);
+    return PCF_OK;
+}
+
+void fill_desc(FrameDesc& d, const float* dev_pts, uint32_t n, uint32_t frame_idx, uint32_t chunk_base, const double* pose) {
+    d.pts = dev_pts;
+    d.n = n;
+    d.frame_idx = frame_idx;
+    d.chunk_base = chunk_base;
+    d.pad = 0;
+    for (int i = 0; i < 12; i++) d.T[i] = pose[i];
+}
+
+// (cell, slot) pairs sorted by cell, stable in slot order; then the sorted point stream and per-voxel CSR
+int prepare_sorted(pcf_ctx* c) {
+    if (c->sorted_valid) return PCF_OK;
+    int rc = flush_holders(c);
+    if (rc) return rc;
+    rc = build_occupancy(c);
+    if (rc) return rc;
+    uint32_t* tot = (uint32_t*)c->total_dev.p;
+    // number of kept points
+    uint32_t P = 0;
+    if (c->n_chunks) {
+        rc = reserve(c, c->tmpB, (size_t)c->n_chunks * 4);
+        if (rc) return rc;
+        rc = scan_u32(c, c->chunk_count, (uint32_t*)c->tmpB.p, c->n_chunks, tot);
+        if (rc) return rc;
+        rc = read_total(c, tot, &P);
+        if (rc) return rc;
+    }
+    c->n_points = P;
+    c->stats.points_kept = P;
+    c->stats.occupied_voxels = c->n_vox;
+    rc = reserve(c, c->uv_off, ((size_t)c->n_vox + 1) * 4);
+    if (rc) return rc;
+    rc = reserve(c, c->uv_cell, ((size_t)c->n_vox + 1) * 4);
+    if (rc) return rc;
+    rc = reserve(c, c->nidx, ((size_t)c->n_vox + 1) * 4);
+    if (rc) return rc;
+    if (P == 0) {
+        CU(cudaMemsetAsync(c->uv_off.p, 0, ((size_t)c->n_vox + 1) * 4, c->stream));
+        c->sorted_valid = true;
+        return PCF_OK;
+    }
+    if ((rc = reserve(c, c->keysA, (size_t)P * 4))) return rc;
+    if ((rc = reserve(c, c->keysB, (size_t)P * 4))) return rc;
+    if ((rc = reserve(c, c->valsA, (size_t)P * 4))) return rc;
+    if ((rc = reserve(c, c->valsB, (size_t)P * 4))) return rc;
+    if ((rc = reserve(c, c->sorted, (size_t)P * sizeof(float4)))) return rc;
+
+    int bits = 1;
+    while ((1ull << bits) < c->g.cells) bits++;
+    int passes = (bits + 7) / 8;
+    int per = (bits + passes - 1) / passes;
+    uint32_t mask = (1u << per) - 1;
+    uint32_t tiles_later = div_up(P, kChunk);
+    if ((rc = reserve(c, c->hist, (size_t)256 * std::max(c->n_chunks, tiles_later) * 4))) return rc;
+    uint32_t* hist = (uint32_t*)c->hist.p;
+    uint32_t *kin = nullptr, *vin = nullptr, *kout = (uint32_t*)c->keysA.p, *vout = (uint32_t*)c->valsA.p;
+    for (int p = 0; p < passes; p++) {
+        SortSrc src{};
+        src.log = c->log; src.chunk_count = c->chunk_count; src.keys = kin; src.vals = vin; src.n = P;
+        uint32_t shift = (uint32_t)(p * per);
+        uint32_t nt = p == 0 ? c->n_chunks : tiles_later;
+        if (p == 0) LAUNCH(c, k_sort_hist<true>, nt, kBlock, src, nt, shift, mask, hist);
+        else LAUNCH(c, k_sort_hist<false>, nt, kBlock, src, nt, shift, mask, hist);
+        rc = scan_u32(c, hist, hist, (uint64_t)256 * nt, nullptr);
+        if (rc) return rc;
+        if (p == 0) LAUNCH(c, k_sort_scatter<true>, nt, kBlock, src, nt, shift, mask, hist, kout, vout);
+        else LAUNCH(c, k_sort_scatter<false>, nt, kBlock, src, nt, shift, mask, hist, kout, vout);
+        kin = kout; vin = vout;
+        kout = (kin == (uint32_t*)c->keysA.p) ? (uint32_t*)c->keysB.p : (uint32_t*)c->keysA.p;
+        vout = (vin == (uint32_t*)c->valsA.p) ? (uint32_t*)c->valsB.p : (uint32_t*)c->valsA.p;
+    }
+    LAUNCH(c, k_gather_points, div_up(P, kBlock), kBlock, c->log, vin, (uint64_t)P, (float4*)c->sorted.p);
+    LAUNCH(c, k_segment_heads, div_up(P, kBlock), kBlock, kin, (uint64_t)P, c->occ_bits, c->occ_rank, (uint32_t*)c->uv_cell.p,
+           (uint32_t*)c->uv_off.p, c->n_vox);
+    CU(cudaGetLastError());
+    c->sorted_valid = true;
+    return PCF_OK;
+}
+
+// scoring of every voxel that has a normal -> sc_a (centroid,count) sc_b (sd,mean_dist) sc_c (sd_dist); nidx map
+int run_scoring(pcf_ctx* c) {
+    int rc = prepare_sorted(c);
+    if (rc) return rc;
+    if (c->n_vox) CU(cudaMemsetAsync(c->nidx.p, 0xFF, (size_t)c->n_vox * 4, c->stream));
+    uint32_t nn = c->n_normals;
+    c->stats.normals_found = nn;
+    if (!nn) return PCF_OK;
+    if ((rc = reserve(c, c->sc_a, (size_t)nn * 16))) return rc;
+    if ((rc = reserve(c, c->sc_b, (size_t)nn * 16))) return rc;
+    if ((rc = reserve(c, c->sc_c, (size_t)nn * 4))) return rc;
+    LAUNCH(c, k_map_normals, div_up(nn, kBlock), kBlock, (const uint32_t*)c->n_cell.p, nn, c->occ_bits, c->occ_rank, (uint32_t*)c->nidx.p);
+    ScoreOut so{(float4*)c->sc_a.p, (float4*)c->sc_b.p, (float*)c->sc_c.p};
+    LAUNCH(c, k_score, div_up(nn, 128), 128, (const uint32_t*)c->n_cell.p, (const float4*)c->n_nrm.p, (const uint32_t*)c->n_mark.p, nn,
+           c->g, c->occ_bits, c->occ_rank, (const uint32_t*)c->uv_off.p, (const uint32_t*)c->nidx.p, (const float4*)c->sorted.p,
+           (const uint32_t*)c->holder, so);
+    CU(cudaGetLastError());
+    return PCF_OK;
+}
+
+int ensure_pinned(pcf_ctx* c, void** p, size_t* cap, size_t bytes) {
+    if (bytes <= *cap) return PCF_OK;
+    if (*p) CU(cudaFreeHost(*p));
+    *p = nullptr; *cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    CU(cudaMallocHost(p, want));
+    *cap = want;
+    return PCF_OK;
+}
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int extract_impl(pcf_ctx* c, int32_t min_count, pcf_result* out) {
+    if (!out) return fail(c, PCF_ERR_INVALID, "null result");
+    memset(out, 0, sizeof *out);
+    CU(cudaEventRecord(c->ev_a, c->stream));
+    int rc = run_scoring(c);
+    if (rc) return rc;
+    uint32_t n_out = 0;
+    uint32_t nv = c->n_vox;
+    if (nv && c->n_normals) {
+        if ((rc = reserve(c, c->flags, (size_t)nv * 4))) return rc;
+        if ((rc = reserve(c, c->slots, (size_t)nv * 4))) return rc;
+        LAUNCH(c, k_extract_flags, div_up(nv, kBlock), kBlock, (const uint32_t*)c->uv_cell.p, nv, (const uint32_t*)c->nidx.p,
+               (const float4*)c->sc_a.p, c->g, min_count, (uint32_t*)c->flags.p);
+        uint32_t* tot = (uint32_t*)c->total_dev.p;
+        if ((rc = scan_u32(c, (uint32_t*)c->flags.p, (uint32_t*)c->slots.p, nv, tot))) return rc;
+        if ((rc = read_total(c, tot, &n_out))) return rc;
+    }
+    // device + host SoA blocks: hash(8) centroid(12) normal(12) sd(12) mean(4) sdd(4) count(4)
+    size_t n = n_out;
+    size_t o_hash = 0, o_cen = align256(o_hash + n * 8), o_nrm = align256(o_cen + n * 12), o_sd = align256(o_nrm + n * 12),
+           o_md = align256(o_sd + n * 12), o_sdd = align256(o_md + n * 4), o_cnt = align256(o_sdd + n * 4), total = align256(o_cnt + n * 4);
+    if ((rc = reserve(c, c->res_dev, total))) return rc;
+    if ((rc = ensure_pinned(c, &c->res_host, &c->res_host_cap, total))) return rc;
+    char* d = (char*)c->res_dev.p;
+    if (n) {
+        ResultDev r{(uint64_t*)(d + o_hash), (float*)(d + o_cen), (float*)(d + o_nrm), (float*)(d + o_sd), (float*)(d + o_md),
+                    (float*)(d + o_sdd), (int32_t*)(d + o_cnt)};
+        LAUNCH(c, k_extract_gather, div_up(nv, kBlock), kBlock, (const uint32_t*)c->uv_cell.p, nv, (const uint32_t*)c->nidx.p,
+               (const uint32_t*)c->flags.p, (const uint32_t*)c->slots.p, (const float4*)c->n_nrm.p, (const float4*)c->sc_a.p,
+               (const float4*)c->sc_b.p, (const float*)c->sc_c.p, c->g, r);
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(c->ev_b, c->stream));
+    if (n) {
+        CU(cudaMemcpyAsync(c->res_host, d, total, cudaMemcpyDeviceToHost, c->stream));
+        c->stats.d2h_bytes += total;
+    }
+    CU(cudaEventRecord(c->ev_c, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaEventElapsedTime(&c->t_extract_dev, c->ev_a, c->ev_b));
+    CU(cudaEventElapsedTime(&c->t_extract_d2h, c->ev_b, c->ev_c));
+    char* h = (char*)c->res_host;
+    out->n = n;
+    out->hash = (const uint64_t*)(h + o_hash);
+    out->centroid = (const float*)(h + o_cen);
+    out->normal = (const float*)(h + o_nrm);
+    out->sd = (const float*)(h + o_sd);
+    out->mean_dist = (const float*)(h + o_md);
+    out->sd_dist = (const float*)(h + o_sdd);
+    out->count = (const int32_t*)(h + o_cnt);
+    return PCF_OK;
+}
+
+void destroy_impl(pcf_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    DevBuf* bufs[] = {&c->n_cell, &c->n_nrm, &c->n_mark, &c->scan1, &c->scan2, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->hist,
+                      &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->sorted, &c->uv_cell, &c->uv_off, &c->nidx, &c->sc_a, &c->sc_b,
+                      &c->sc_c, &c->flags, &c->slots, &c->cand, &c->res_dev, &c->total_dev};
+    for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    void* raw[] = {c->first_frame, c->holder, c->nrm_bits, c->occ_bits, c->occ_rank, c->vp_table, c->log, c->chunk_count, c->desc_dev};
+    for (void* p : raw) if (p) cudaFree(p);
+    for (int i = 0; i < kRing; i++) {
+        if (c->stage[i]) cudaFree(c->stage[i]);
+        if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+        if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
+    }
+    if (c->desc_host) cudaFreeHost(c->desc_host);
+    if (c->total_host) cudaFreeHost(c->total_host);
+    if (c->res_host) cudaFreeHost(c->res_host);
+    if (c->st_host) cudaFreeHost(c->st_host);
+    cudaEvent_t evs[] = {c->ev_desc, c->ev_a, c->ev_b, c->ev_c};
+    for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+int reset_grid_state(pcf_ctx* c) {
+    CU(cudaMemsetAsync(c->first_frame, 0xFF, c->g.cells * 4, c->stream));
+    CU(cudaMemsetAsync(c->nrm_bits, 0, (c->n_words + 2) * 4, c->stream));
+    CU(cudaMemsetAsync(c->occ_bits, 0, (c->n_words + 2) * 4, c->stream));
+    CU(cudaMemsetAsync(c->vp_table, 0, (size_t)c->cfg.max_frames * sizeof(float4), c->stream));
+    if (c->holder) CU(cudaMemsetAsync(c->holder, 0, c->g.cells * 4, c->stream));
+    c->n_chunks = 0;
+    c->n_normals = 0;
+    c->n_vox = 0;
+    c->n_points = 0;
+    c->marks.clear();
+    c->pending_holder.clear();
+    c->occ_dirty = true;
+    c->sorted_valid = false;
+    c->last_frame_idx = -1;
+    return PCF_OK;
+}
+
+}  // namespace
+
+// ============================================ C ABI ===================================================
+extern "C" {
+
+void pcf_default_config(pcf_config* cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof *cfg);
+    const double box[6] = {-0.8, 1.8, -1.5, 1.5, 0.0, 1.0};   // launch:8
+    memcpy(cfg->box, box, sizeof box);
+    cfg->res[0] = cfg->res[1] = cfg->res[2] = (float)0.005;   // node.cpp:91,161
+    cfg->clip_zmin = 0.28;                                    // node.cpp:92
+    cfg->clip_zmax = 0.6;                                     // node.cpp:93
+    cfg->k_neighbourhood = 2;                                 // node.cpp:163
+    cfg->walk_k = 3;                                          // node.cpp:311
+    cfg->min_neighbours = 20;                                 // OG.hpp:352
+    cfg->cylinder_radius = 0.001;                             // OG.hpp:36
+    cfg->ball_radius = 0.015;                                 // OG.hpp:35
+    cfg->device = 0;
+    cfg->max_frames = 1u << 16;
+    cfg->log_capacity_hint = 0;
+}
+
+int pcf_create(const pcf_config* cfg, pcf_ctx** out) {
+    pcf_ctx* c = nullptr;
+    if (!cfg || !out) return fail(c, PCF_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(c, PCF_ERR_NO_DEVICE, "no CUDA device: libpcfusion has no CPU path");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(c, PCF_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
+    pcf_ctx* ctx = new pcf_ctx();
+    ctx->cfg = *cfg;
+    if (ctx->cfg.max_frames == 0) ctx->cfg.max_frames = 1u << 16;
+    ctx->device = cfg->device;
+    int rc = build_grid_params(ctx);
+    if (rc) { g_create_error = ctx->err; delete ctx; return rc; }
+    c = ctx;
+    auto bail = [&](int code) { g_create_error = ctx->err; destroy_impl(ctx); return code; };
+#define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, PCF_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(PCF_ERR_CUDA); } } while (0)
+    CUC(cudaSetDevice(c->device));
+    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    c->n_words = (c->g.cells + 31) / 32;
+    CUC(cudaMalloc(&c->first_frame, c->g.cells * 4));
+    CUC(cudaMalloc(&c->nrm_bits, (c->n_words + 2) * 4));
+    CUC(cudaMalloc(&c->occ_bits, (c->n_words + 2) * 4));
+    CUC(cudaMalloc(&c->occ_rank, (c->n_words + 2) * 4));
+    CUC(cudaMalloc(&c->vp_table, (size_t)c->cfg.max_frames * sizeof(float4)));
+    CUC(cudaMallocHost(&c->total_host, 64));
+    for (int i = 0; i < kRing; i++) {
+        CUC(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
+    }
+    CUC(cudaEventCreateWithFlags(&c->ev_desc, cudaEventDisableTiming));
+    CUC(cudaEventCreate(&c->ev_a));
+    CUC(cudaEventCreate(&c->ev_b));
+    CUC(cudaEventCreate(&c->ev_c));
+    if (reserve(c, c->total_dev, 64)) return bail(PCF_ERR_CUDA);
+    if (reset_grid_state(c)) return bail(PCF_ERR_CUDA);
+    uint64_t hint = cfg->log_capacity_hint ? cfg->log_capacity_hint : (uint64_t)64 * 307200;
+    if (ensure_log(c, std::min<uint64_t>(div_up(hint, kChunk) + 1, kMaxChunks))) return bail(PCF_ERR_CUDA);
+    CUC(cudaStreamSynchronize(c->stream));
+#undef CUC
+    *out = c;
+    return PCF_OK;
+}
+
+void pcf_destroy(pcf_ctx* ctx) { destroy_impl(ctx); }
+
+const char* pcf_last_error(const pcf_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int pcf_dims(const pcf_ctx* ctx, int32_t dims[3]) {
+    if (!ctx || !dims) return PCF_ERR_INVALID;
+    for (int a = 0; a < 3; a++) dims[a] = ctx->g.dim[a];
+    return PCF_OK;
+}
+
+int pcf_start(pcf_ctx* c) { if (!c) return PCF_ERR_INVALID; c->started = true; return PCF_OK; }
+int pcf_stop(pcf_ctx* c) { if (!c) return PCF_ERR_INVALID; c->started = false; return PCF_OK; }
+int pcf_reset(pcf_ctx* c) {
+    // node.cpp:351-359 clears the not-yet-processed input deque and leaves the grid alone.  Frames handed to
+    // pcf_push_* are already queued on the device, which corresponds to "already popped by the worker thread";
+    // there is no host-side backlog to drop, so reset only has to keep the service contract (grid untouched).
+    if (!c) return PCF_ERR_INVALID;
+    return PCF_OK;
+}
+
+int pcf_push_frame(pcf_ctx* c, const float* pts_host, uint32_t n, uint32_t stride, const double pose[16], uint32_t frame_idx) {
+    if (!c) return PCF_ERR_INVALID;
+    if (!c->started) return PCF_DROPPED;
+    if ((!pts_host && n) || !pose || stride < 3) return fail(c, PCF_ERR_INVALID, "bad frame arguments");
+    int rc = check_frame_idx(c, frame_idx, 1);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    if ((rc = flush_holders(c))) return rc;
+    uint32_t chunks = div_up(n, kChunk);
+    if ((rc = ensure_log(c, c->n_chunks + chunks))) return rc;
+    int s = c->ring_pos;
+    c->ring_pos = (c->ring_pos + 1) % kRing;
+    size_t bytes = (size_t)n * stride * 4;
+    if (bytes > c->stage_cap[s]) {
+        CU(cudaEventSynchronize(c->ev_free[s]));
+        if (c->stage[s]) CU(cudaFree(c->stage[s]));
+        c->stage[s] = nullptr;
+        CU(cudaMalloc(&c->stage[s], bytes + bytes / 4));
+        c->stage_cap[s] = bytes + bytes / 4;
+    }
+    // copy stream: wait until the kernel that last read this slot is done, then upload
+    CU(cudaStreamWaitEvent(c->copy_stream, c->ev_free[s], 0));
+    if (bytes) CU(cudaMemcpyAsync(c->stage[s], pts_host, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaEventRecord(c->ev_copied[s], c->copy_stream));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_copied[s], 0));
+    FrameDesc d;
+    fill_desc(d, c->stage[s], n, frame_idx, c->n_chunks, pose);
+    if (chunks) {
+        rc = launch_ingest<false>(c, stride, dim3(chunks, 1, 1), nullptr, d);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(c->ev_free[s], c->stream));
+    c->n_chunks += chunks;
+    c->last_frame_idx = frame_idx;
+    c->occ_dirty = true;
+    c->sorted_valid = false;
+    c->stats.frames_pushed++;
+    c->stats.points_offered += n;
+    c->stats.h2d_bytes += bytes;
+    return PCF_OK;
+}
+
+int pcf_push_frames_device(pcf_ctx* c, const float* pts_dev, uint32_t n_frames, uint32_t n_per_frame, uint32_t stride,
+                           const double* poses, uint32_t first_frame_idx) {
+    if (!c) return PCF_ERR_INVALID;
+    if (!c->started) return PCF_DROPPED;
+    if (!n_frames) return PCF_OK;
+    if (!pts_dev || !poses || stride < 3) return fail(c, PCF_ERR_INVALID, "bad frame arguments");
+    int rc = check_frame_idx(c, first_frame_idx, n_frames);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    if ((rc = flush_holders(c))) return rc;
+    uint32_t chunks = div_up(n_per_frame, kChunk);
+    if ((uint64_t)c->n_chunks + (uint64_t)chunks * n_frames > kMaxChunks) return fail(c, PCF_ERR_CAPACITY, "point log limit reached");
+    if ((rc = ensure_log(c, c->n_chunks + chunks * n_frames))) return rc;
+    if (n_frames > c->desc_cap) {
+        CU(cudaStreamSynchronize(c->stream));
+        if (c->desc_dev) CU(cudaFree(c->desc_dev));
+        if (c->desc_host) CU(cudaFreeHost(c->desc_host));
+        c->desc_dev = nullptr; c->desc_host = nullptr;
+        uint32_t cap = std::max<uint32_t>(n_frames, 256);
+        CU(cudaMalloc(&c->desc_dev, (size_t)cap * sizeof(FrameDesc)));
+        CU(cudaMallocHost(&c->desc_host, (size_t)cap * sizeof(FrameDesc)));
+        c->desc_cap = cap;
+        CU(cudaEventRecord(c->ev_desc, c->stream));
+    }
+    CU(cudaEventSynchronize(c->ev_desc));   // previous batch has consumed the pinned descriptors
+    for (uint32_t f = 0; f < n_frames; f++) {
+        const double* pose = poses + (size_t)f * 16;
+        fill_desc(c->desc_host[f], pts_dev + (size_t)f * n_per_frame * stride, n_per_frame, first_frame_idx + f,
+                  c->n_chunks + f * chunks, pose);
+    }
+    CU(cudaMemcpyAsync(c->desc_dev, c->desc_host, (size_t)n_frames * sizeof(FrameDesc), cudaMemcpyHostToDevice, c->stream));
+    if (chunks) {
+        FrameDesc dummy{};
+        rc = launch_ingest<true>(c, stride, dim3(chunks, n_frames, 1), c->desc_dev, dummy);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(c->ev_desc, c->stream));
+    c->n_chunks += chunks * n_frames;
+    c->last_frame_idx = (int64_t)first_frame_idx + n_frames - 1;
+    c->occ_dirty = true;
+    c->sorted_valid = false;
+    c->stats.frames_pushed += n_frames;
+    c->stats.points_offered += (uint64_t)n_frames * n_per_frame;
+    c->stats.h2d_bytes += (size_t)n_frames * sizeof(FrameDesc);
+    return PCF_OK;
+}
+
+int pcf_sync(pcf_ctx* c) {
+    if (!c) return PCF_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return PCF_OK;
+}
+
+int pcf_update(pcf_ctx* c) {
+    if (!c) return PCF_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->ev_a, c->stream));
+    int rc = flush_holders(c);
+    if (rc) return rc;
+    if ((rc = build_occupancy(c))) return rc;
+    uint32_t mark = c->n_chunks * (uint32_t)kChunk;   // n_chunks <= 2^21 -> fits (2^32 wraps only at the hard limit)
+    if (c->n_chunks >= kMaxChunks) mark = 0xFFFFFFFFu;
+    c->marks.push_back(mark);
+    c->stats.update_passes++;
+    uint32_t n_cand = 0;
+    uint32_t* tot = (uint32_t*)c->total_dev.p;
+    if (c->n_vox) {
+        if ((rc = reserve(c, c->tmpA, (size_t)c->n_words * 4))) return rc;
+        if ((rc = reserve(c, c->tmpB, (size_t)c->n_words * 4))) return rc;
+        uint32_t* cnt = (uint32_t*)c->tmpA.p;
+        uint32_t* off = (uint32_t*)c->tmpB.p;
+        LAUNCH(c, k_cand_count, div_up(c->n_words, kBlock), kBlock, c->occ_bits, c->nrm_bits, c->n_words, cnt);
+        if ((rc = scan_u32(c, cnt, off, c->n_words, tot))) return rc;
+        if ((rc = read_total(c, tot, &n_cand))) return rc;
+        if (n_cand) {
+            if ((rc = reserve(c, c->cand, (size_t)n_cand * 4))) return rc;
+            if ((rc = reserve(c, c->tmpC, (size_t)n_cand * 16))) return rc;
+            if ((rc = reserve(c, c->tmpD, (size_t)n_cand * 8))) return rc;
+            uint32_t* cand = (uint32_t*)c->cand.p;
+            float4* tnrm = (float4*)c->tmpC.p;
+            uint32_t* flag = (uint32_t*)c->tmpD.p;
+            uint32_t* foff = flag + n_cand;
+            LAUNCH(c, k_cand_list, div_up(c->n_words, kBlock), kBlock, c->occ_bits, c->nrm_bits, c->n_words, off, cand);
+            LAUNCH(c, k_normals, div_up(n_cand, kBlock), kBlock, cand, n_cand, c->g, c->occ_bits, c->first_frame, c->vp_table, tnrm, flag);
+            if ((rc = scan_u32(c, flag, foff, n_cand, tot))) return rc;
+            uint32_t n_new = 0;
+            if ((rc = read_total(c, tot, &n_new))) return rc;
+            if (n_new) {
+                size_t need = (size_t)c->n_normals + n_new;
+                if ((rc = reserve(c, c->n_cell, need * 4, true))) return rc;
+                if ((rc = reserve(c, c->n_nrm, need * 16, true))) return rc;
+                if ((rc = reserve(c, c->n_mark, need * 4, true))) return rc;
+                LAUNCH(c, k_append_normals, div_up(n_cand, kBlock), kBlock, cand, n_cand, tnrm, flag, foff, c->n_normals, mark,
+                       (uint32_t*)c->n_cell.p, (float4*)c->n_nrm.p, (uint32_t*)c->n_mark.p, c->nrm_bits);
+                c->pending_holder.emplace_back(c->n_normals, c->n_normals + n_new);
+                c->n_normals += n_new;
+            }
+        }
+    }
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev_b, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaEventElapsedTime(&c->t_update, c->ev_a, c->ev_b));
+    c->stats.normals_found = c->n_normals;
+    c->stats.occupied_voxels = c->n_vox;
+    return PCF_OK;
+}
+
+int pcf_extract(pcf_ctx* c, pcf_result* out) {
+    if (!c) return PCF_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    return extract_impl(c, 0, out);
+}
+
+int pcf_extract_hq(pcf_ctx* c, double threshold, pcf_result* out) {
+    if (!c) return PCF_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    // downloadHQ skips `count < threshold` (OG.hpp:561): for an int count that is count >= ceil(threshold)
+    return extract_impl(c, (int32_t)std::ceil(threshold), out);
+}
+
+int pcf_clear(pcf_ctx* c) {
+    if (!c) return PCF_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    int rc = reset_grid_state(c);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    return PCF_OK;
+}
+
+int pcf_process(pcf_ctx* c, const char* cloud_path, const char* meta_path) {
+    if (!c) return PCF_ERR_INVALID;
+    int rc = pcf_sync(c);                 // node.cpp:380-394: wait until both queues are drained
+    if (rc) return rc;
+    pcf_result r;
+    if ((rc = pcf_extract(c, &r))) return rc;
+    if ((rc = pcf_write_result(&r, cloud_path, meta_path))) return fail(c, rc, "could not write %s / %s", cloud_path ? cloud_path : "-", meta_path ? meta_path : "-");
+    return pcf_clear(c);                  // node.cpp:438
+}
+
+int pcf_dump_state(pcf_ctx* c, pcf_state* out) {
+    if (!c || !out) return PCF_ERR_INVALID;
+    memset(out, 0, sizeof *out);
+    CU(cudaSetDevice(c->device));
+    int rc = run_scoring(c);
+    if (rc) return rc;
+    size_t n = c->n_vox;
+    size_t o_hash = 0, o_len = align256(n * 8), o_cnt = align256(o_len + n * 4), o_nrm = align256(o_cnt + n * 4),
+           o_vp = align256(o_nrm + n * 12), o_nf = align256(o_vp + n * 12), total = align256(o_nf + n);
+    if ((rc = reserve(c, c->res_dev, total))) return rc;
+    if ((rc = ensure_pinned(c, &c->st_host, &c->st_host_cap, total))) return rc;
+    char* d = (char*)c->res_dev.p;
+    if (n) {
+        StateDev s{(uint64_t*)(d + o_hash), (int32_t*)(d + o_len), (uint8_t*)(d + o_nf), (int32_t*)(d + o_cnt), (float*)(d + o_nrm), (float*)(d + o_vp)};
+        LAUNCH(c, k_dump_state, div_up(n, kBlock), kBlock, (const uint32_t*)c->uv_cell.p, (const uint32_t*)c->uv_off.p, (uint32_t)n,
+               (const uint32_t*)c->nidx.p, (const uint32_t*)c->n_mark.p, (const float4*)c->n_nrm.p, (const float4*)c->sc_a.p,
+               (const float4*)c->sorted.p, c->first_frame, c->vp_table, c->g, s);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(c->st_host, d, total, cudaMemcpyDeviceToHost, c->stream));
+        c->stats.d2h_bytes += total;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    char* h = (char*)c->st_host;
+    out->n = n;
+    out->hash = (const uint64_t*)(h + o_hash);
+    out->buffer_len = (const int32_t*)(h + o_len);
+    out->normal_found = (const uint8_t*)(h + o_nf);
+    out->count = (const int32_t*)(h + o_cnt);
+    out->normal = (const float*)(h + o_nrm);
+    out->viewpoint = (const float*)(h + o_vp);
+    return PCF_OK;
+}
+
+int pcf_get_stats(pcf_ctx* c, pcf_stats* out) {
+    if (!c || !out) return PCF_ERR_INVALID;
+    *out = c->stats;
+    return PCF_OK;
+}
+int pcf_reset_stats(pcf_ctx* c) {
+    if (!c) return PCF_ERR_INVALID;
+    c->stats = pcf_stats{};
+    return PCF_OK;
+}
+int pcf_last_timings(pcf_ctx* c, float* update_ms, float* extract_device_ms, float* extract_d2h_ms) {
+    if (!c) return PCF_ERR_INVALID;
+    if (update_ms) *update_ms = c->t_update;
+    if (extract_device_ms) *extract_device_ms = c->t_extract_dev;
+    if (extract_d2h_ms) *extract_d2h_ms = c->t_extract_d2h;
+    return PCF_OK;
+}
+void* pcf_stream(pcf_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+// ---- multi-GPU hooks ---------------------------------------------------------------------------------
+int pcf_grid_buffer(pcf_ctx* c, void** first_frame_dev, uint64_t* n_cells) {
+    if (!c || !first_frame_dev || !n_cells) return PCF_ERR_INVALID;
+    *first_frame_dev = c->first_frame;
+    *n_cells = c->g.cells;
+    c->occ_dirty = true;        // the caller is about to reduce into it
+    c->sorted_valid = false;
+    return PCF_OK;
+}
+int pcf_viewpoint_table(pcf_ctx* c, void** vp_dev, uint32_t* max_frames) {
+    if (!c || !vp_dev || !max_frames) return PCF_ERR_INVALID;
+    *vp_dev = c->vp_table;
+    *max_frames = c->cfg.max_frames;
+    return PCF_OK;
+}
+int pcf_log_compact(pcf_ctx* c, void** log_dev, uint64_t* n_points) {
+    return c ? fail(c, PCF_ERR_INVALID, "pcf_log_compact: not implemented yet") : PCF_ERR_INVALID;
+}
+int pcf_log_replace(pcf_ctx* c, const void* log_dev, uint64_t n_points) {
+    return c ? fail(c, PCF_ERR_INVALID, "pcf_log_replace: not implemented yet") : PCF_ERR_INVALID;
+}
+
+// ---- known-answer hooks -------------------------------------------------------------------------------
+int pcf_kat_transform_voxel(pcf_ctx* c, const float* pts_host, uint32_t n, uint32_t stride, const double pose[16],
+                            float* world_xyz, int32_t* ijk, uint8_t* kept) {
+    if (!c || !pts_host || !pose || stride < 3) return PCF_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    float* d_in; float* d_w; int32_t* d_ijk; uint8_t* d_k;
+    CU(cudaMalloc(&d_in, (size_t)n * stride * 4));
+    CU(cudaMalloc(&d_w, (size_t)n * 12));
+    CU(cudaMalloc(&d_ijk, (size_t)n * 12));
+    CU(cudaMalloc(&d_k, (size_t)n));
+    CU(cudaMemcpyAsync(d_in, pts_host, (size_t)n * stride * 4, cudaMemcpyHostToDevice, c->stream));
+    FrameDesc fd;
+    fill_desc(fd, d_in, n, 0, 0, pose);
+    LAUNCH(c, k_kat_transform_voxel, div_up(n, 256), 256, d_in, n, stride, fd, c->g, d_w, d_ijk, d_k);
+    CU(cudaMemcpyAsync(world_xyz, d_w, (size_t)n * 12, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(ijk, d_ijk, (size_t)n * 12, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(kept, d_k, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d_in); cudaFree(d_w); cudaFree(d_ijk); cudaFree(d_k);
+    return PCF_OK;
+}
+int pcf_kat_normal(pcf_ctx* c, const float* xyz_host, uint32_t n_points, float* normal3) {
+    if (!c || !xyz_host || !normal3) return PCF_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    float *d_in, *d_out;
+    CU(cudaMalloc(&d_in, (size_t)n_points * 12));
+    CU(cudaMalloc(&d_out, 12));
+    CU(cudaMemcpyAsync(d_in, xyz_host, (size_t)n_points * 12, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, k_kat_normal, 1, 32, d_in, n_points, d_out);
+    CU(cudaMemcpyAsync(normal3, d_out, 12, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d_in); cudaFree(d_out);
+    return PCF_OK;
+}
+int pcf_kat_score(pcf_ctx* c, const float* xyz_host, uint32_t n_points, const float axis_pt[3], const float normal[3],
+                  float* centroid3, float* sd3, float* mean_dist, float* sd_dist, int32_t* count) {
+    if (!c || !xyz_host) return PCF_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    float *d_in, *d_out; int32_t* d_cnt;
+    CU(cudaMalloc(&d_in, (size_t)n_points * 12 + 4));
+    CU(cudaMalloc(&d_out, 64));
+    CU(cudaMalloc(&d_cnt, 4));
+    CU(cudaMemcpyAsync(d_in, xyz_host, (size_t)n_points * 12, cudaMemcpyHostToDevice, c->stream));
+    V3 a{axis_pt[0], axis_pt[1], axis_pt[2]}, nn{normal[0], normal[1], normal[2]};
+    LAUNCH(c, k_kat_score, 1, 32, d_in, n_points, a, nn, c->g, d_out, d_cnt);
+    float h[9];
+    CU(cudaMemcpyAsync(h, d_out, 32, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(count, d_cnt, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(centroid3, h, 12); memcpy(sd3, h + 3, 12); *mean_dist = h[6]; *sd_dist = h[7];
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_cnt);
+    return PCF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,161 @@
+/* pcfusion.h -- C ABI of libpcfusion.so, the B200 (sm_100a) drop-in for the frame-integration and
+ * process() hot path of the `pointcloud_fusion` node (REXJJ/high-fidelity-pointcloud-fusion).
+ *
+ * The reference has no FFI layer: its boundary is the public surface of `class OccupancyGrid`
+ * (OG.hpp = pointcloud_fusion/pointcloud_fusion/include/utilities/OccupancyGrid.hpp:99-136) as driven by
+ * `PointcloudFusion` (node.cpp = pointcloud_fusion/pointcloud_fusion/src/pointcloud_fusion_and_filter.cpp).
+ * Every entry point below names the reference interface it replaces.  Plain pointers and sizes only.
+ *
+ * Threading: like the reference grid (serialised by grid_mtx_, node.cpp:291-296,305-321) one context must be
+ * driven from one thread at a time.  pcf_push_* are asynchronous on the context's CUDA stream; pcf_sync,
+ * pcf_update (results), pcf_extract, pcf_dump_state, pcf_process and pcf_clear synchronise.
+ * Errors: every call returns PCF_OK (0) or a negative pcf_status; nothing throws across this boundary.
+ */
+#ifndef PCFUSION_H
+#define PCFUSION_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pcf_ctx pcf_ctx;
+
+typedef enum {
+    PCF_OK = 0,
+    PCF_DROPPED = 1,          /* frame offered while stopped: ignored, like node.cpp:329-331 */
+    PCF_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
+    PCF_ERR_CUDA = -2,        /* CUDA runtime error (text in pcf_last_error) */
+    PCF_ERR_CAPACITY = -3,    /* point log / frame table limit reached */
+    PCF_ERR_IO = -4,          /* cloud / metadata file could not be written */
+    PCF_ERR_NO_DEVICE = -5    /* no usable CUDA device: the library has no CPU fallback */
+} pcf_status;
+
+/* Grid + stage parameters.  Replaces the compile-time constants and ctor calls of the node:
+ *   box      setDimensions(xmin,xmax,ymin,ymax,zmin,zmax)  OG.hpp:604-612, node.cpp:162, launch:8
+ *   res      setResolution(float,float,float)              OG.hpp:614-619, node.cpp:91,161 (float on purpose:
+ *            dims = (int)((max-min)/double(res)) keeps the reference's truncation, OG.hpp:621-626)
+ *   clip_*   kZmin / kZmax camera-frame depth clip          node.cpp:92-93,251
+ *   k_neighbourhood  setK(2): 5x5x5 probe block             OG.hpp:138-149,334 (only 2 is supported, D9)
+ *   walk_k   K of updateThicknessVectors<N,K>               node.cpp:311, OG.hpp:403
+ *   min_neighbours   `total>20` gate                        OG.hpp:352
+ *   cylinder_radius / ball_radius  kCylinderRadius / kBballRadius   OG.hpp:35-36
+ */
+typedef struct {
+    double box[6];
+    float res[3];
+    double clip_zmin, clip_zmax;
+    int32_t k_neighbourhood;
+    int32_t walk_k;
+    int32_t min_neighbours;
+    double cylinder_radius;
+    double ball_radius;
+    int32_t device;              /* CUDA device ordinal */
+    uint32_t max_frames;         /* size of the frame/viewpoint table (frame_idx < max_frames) */
+    uint64_t log_capacity_hint;  /* initial point-log capacity in INPUT points; grows on demand */
+} pcf_config;
+
+/* Extraction output, structure of arrays, x-major voxel order = the reference's scan order
+ * (downloadData, OG.hpp:463-480).  Host memory owned by the library, valid until the next
+ * pcf_extract / pcf_process / pcf_clear / pcf_destroy on the same context. */
+typedef struct {
+    uint64_t n;
+    const uint64_t* hash;     /* getHashId(x,y,z), OG.hpp:151-156 */
+    const float* centroid;    /* n x 3, VoxelInfo::centroid (mean of projected in-cylinder points) */
+    const float* normal;      /* n x 3 */
+    const float* sd;          /* n x 3 */
+    const float* mean_dist;   /* n */
+    const float* sd_dist;     /* n */
+    const int32_t* count;     /* n, points inside the 1 mm normal cylinder */
+} pcf_result;
+
+/* Per-voxel state for parity tests: every occupied cell (pad cells index==dim included), x-major. */
+typedef struct {
+    uint64_t n;
+    const uint64_t* hash;
+    const int32_t* buffer_len;    /* VoxelInfo::buffer.size(), OG.hpp:70,211 */
+    const uint8_t* normal_found;  /* OG.hpp:72 */
+    const int32_t* count;         /* OG.hpp:73 */
+    const float* normal;          /* n x 3 (zeros where !normal_found) */
+    const float* viewpoint;       /* n x 3, first inserting frame's viewpoint, OG.hpp:229 */
+} pcf_state;
+
+typedef struct {
+    uint64_t frames_pushed;
+    uint64_t points_offered;      /* input points incl. clipped / cropped ones */
+    uint64_t points_kept;         /* passed z clip and box test (valid after pcf_sync) */
+    uint64_t occupied_voxels;     /* valid after pcf_extract / pcf_dump_state */
+    uint64_t normals_found;
+    uint64_t kernel_launches;     /* library kernels launched since create / last pcf_reset_stats */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint32_t update_passes;
+} pcf_stats;
+
+void pcf_default_config(pcf_config* cfg);       /* launch-file defaults: launch:4-8, node.cpp:91-93 */
+int pcf_create(const pcf_config* cfg, pcf_ctx** out);   /* ctor + setResolution/setDimensions/setK/construct, node.cpp:146-169 */
+void pcf_destroy(pcf_ctx* ctx);
+const char* pcf_last_error(const pcf_ctx* ctx);  /* ctx may be NULL: error of the last failed pcf_create */
+int pcf_dims(const pcf_ctx* ctx, int32_t dims[3]);      /* xdim_,ydim_,zdim_  OG.hpp:621-625 */
+
+/* Service semantics (std_srvs/Trigger handlers). */
+int pcf_start(pcf_ctx* ctx);    /* node.cpp:361-367 */
+int pcf_stop(pcf_ctx* ctx);     /* node.cpp:369-375: queued frames still integrate */
+int pcf_reset(pcf_ctx* ctx);    /* node.cpp:351-359: drops not-yet-integrated input, keeps the grid */
+
+/* Frame integration = onReceivedPointCloud -> addPoints thread (z clip) -> updateStates thread
+ * (transformPointCloud + OccupancyGrid::addPoints): node.cpp:327-349, 248-255, 288-296, OG.hpp:185-280.
+ * pts: n points, `stride_floats` floats apart (>=3; 4 = float4 fast path), camera frame, host memory
+ * (pinned for full speed).  pose: row-major 4x4 fusion<-camera (Eigen::Affine3d of node.cpp:338).
+ * frame_idx must increase from call to call on one context.  Returns PCF_DROPPED while stopped. */
+int pcf_push_frame(pcf_ctx* ctx, const float* pts_host, uint32_t n, uint32_t stride_floats,
+                   const double pose[16], uint32_t frame_idx);
+/* Same for clouds already resident in device memory: n_frames clouds of n_per_frame points each, back to
+ * back, integrated by ONE launch.  poses: n_frames x 16 doubles (host).  Frames get indices
+ * first_frame_idx .. first_frame_idx+n_frames-1. */
+int pcf_push_frames_device(pcf_ctx* ctx, const float* pts_dev, uint32_t n_frames, uint32_t n_per_frame,
+                           uint32_t stride_floats, const double* poses, uint32_t first_frame_idx);
+int pcf_sync(pcf_ctx* ctx);     /* wait for all queued integration work */
+
+/* updateThicknessVectors<N,K>(): neighbour scan, PCA normal, +-K walk registration.  OG.hpp:311-454,
+ * called by the cleanGrid thread every 5 s (node.cpp:301-325); here the schedule is explicit (D4). */
+int pcf_update(pcf_ctx* ctx);
+
+/* Scoring + x-major stream-compacted extraction; does not modify the grid.  OG.hpp:456-488 (scan part). */
+int pcf_extract(pcf_ctx* ctx, pcf_result* out);
+/* getFusedCloud(): drain, downloadData(cloud_path, meta_path) as ASCII PCD + CSV, clearVoxels().
+ * node.cpp:377-440, OG.hpp:456-488, 167-183.  Paths may be NULL to skip a file. */
+int pcf_process(pcf_ctx* ctx, const char* cloud_path, const char* meta_path);
+int pcf_write_result(const pcf_result* res, const char* cloud_path, const char* meta_path);
+/* Dead-code variants kept by the reference (OG.hpp:514-575, node.cpp:399-437): same scan with a predicate.
+ * Returns in `out` only voxels with count >= threshold (downloadHQ). */
+int pcf_extract_hq(pcf_ctx* ctx, double threshold, pcf_result* out);
+int pcf_clear(pcf_ctx* ctx);    /* clearVoxels() + work lists, OG.hpp:167-183 (D5: full reset) */
+
+int pcf_dump_state(pcf_ctx* ctx, pcf_state* out);
+int pcf_get_stats(pcf_ctx* ctx, pcf_stats* out);
+int pcf_reset_stats(pcf_ctx* ctx);
+/* Milliseconds spent on the device by the last pcf_update / pcf_extract (CUDA events on the ctx stream). */
+int pcf_last_timings(pcf_ctx* ctx, float* update_ms, float* extract_device_ms, float* extract_d2h_ms);
+/* CUDA stream of the context as a cudaStream_t (for callers that time with their own events). */
+void* pcf_stream(pcf_ctx* ctx);
+
+/* ---- multi-GPU merge hooks (one context per GPU; the exchange itself is the caller's, e.g. NCCL) --------
+ * Frames are sharded over ranks in contiguous frame_idx blocks.  At process() the dense first-frame grid is
+ * min-reduced across ranks, viewpoints are all-gathered, and each rank's point log is exchanged. */
+int pcf_grid_buffer(pcf_ctx* ctx, void** first_frame_dev, uint64_t* n_cells);    /* uint32 per cell, 0xFFFFFFFF = empty */
+int pcf_viewpoint_table(pcf_ctx* ctx, void** vp_dev, uint32_t* max_frames);       /* float4 per frame_idx, w=1 when set */
+int pcf_log_compact(pcf_ctx* ctx, void** log_dev, uint64_t* n_points);            /* float4 (x,y,z,cell) in arrival order */
+int pcf_log_replace(pcf_ctx* ctx, const void* log_dev, uint64_t n_points);        /* install a merged log (arrival order) */
+
+/* ---- known-answer hooks: run ONE device function over an array (tests bit-compare with the oracle) ---- */
+int pcf_kat_transform_voxel(pcf_ctx* ctx, const float* pts_host, uint32_t n, uint32_t stride_floats,
+                            const double pose[16], float* world_xyz, int32_t* ijk, uint8_t* kept);
+int pcf_kat_normal(pcf_ctx* ctx, const float* xyz_host, uint32_t n_points, float* normal3);
+int pcf_kat_score(pcf_ctx* ctx, const float* xyz_host, uint32_t n_points, const float axis_pt[3],
+                  const float normal[3], float* centroid3, float* sd3, float* mean_dist, float* sd_dist,
+                  int32_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCFUSION_H */

@@ -1,0 +1,154 @@
+"""GPU parity tests: libpcfusion.so (through its C ABI) against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from helpers import RESULT_FIELDS, STATE_FIELDS, assert_result_parity, assert_same, bits_equal, run_schedule
+
+pytestmark = pytest.mark.gpu
+
+
+def _synth(pcf):
+    import importlib
+    return importlib.import_module(pcf.__name__ + ".synth")
+
+
+@pytest.fixture(scope="module")
+def small(pcf):
+    return _synth(pcf).small_sphere(6)
+
+
+def test_kat_transform_clip_box_voxel(pcf, oracle):
+    """a2/a3/a6: z clip, FP64 transform narrowed to float, strict box test, floor((p-min)/res)."""
+    rng = np.random.default_rng(0)
+    box, res = (-0.25, 0.25) * 3, 0.001
+    fus = pcf.Fusion(box, res)
+    og = oracle.OracleGrid(box, res)
+    n = 200000
+    pts = np.zeros((n, 4), np.float32)
+    pts[:, :3] = rng.uniform(-0.3, 0.3, (n, 3))
+    pts[:, 2] = rng.uniform(0.25, 0.65, n)
+    # adversarial: exact clip limits, NaNs, points on voxel borders
+    pts[:50, 2] = np.float32(0.28); pts[50:100, 2] = np.float32(0.6); pts[100:150, 2] = np.nan
+    pts[150:160, 0] = np.nan
+    ang = 0.3
+    T = np.eye(4); T[:3, :3] = [[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]]; T[:3, 3] = [0.01, -0.02, -0.45]
+    w, ijk, kept = fus.kat_transform_voxel(pts, T)
+    clip = (pts[:, 2].astype(np.float64) < 0.6) & (pts[:, 2].astype(np.float64) > 0.28)
+    w_ref = oracle.kat_transform(T, pts)
+    ijk_ref, valid_ref = oracle.kat_voxel(og, w_ref)
+    keep_ref = clip & (valid_ref == 1)
+    assert np.array_equal(kept.astype(bool), keep_ref)
+    assert bits_equal(w[keep_ref], w_ref[keep_ref])
+    assert np.array_equal(ijk[keep_ref], ijk_ref[keep_ref])
+    # identity pose with world points exactly on cell borders / box faces
+    k = rng.integers(0, 500, (20000, 3))
+    border = (-0.25 + k * np.float64(np.float32(res))).astype(np.float32)
+    border[:, 2] = np.clip(border[:, 2], 0.2801, 0.5999)  # must survive the clip (pose is identity)
+    og2 = oracle.OracleGrid((-0.25, 0.25, -0.25, 0.25, 0.0, 1.0), res)
+    fus2 = pcf.Fusion((-0.25, 0.25, -0.25, 0.25, 0.0, 1.0), res)
+    p4 = np.zeros((len(border), 4), np.float32); p4[:, :3] = border
+    w2, ijk2, kept2 = fus2.kat_transform_voxel(p4, np.eye(4))
+    ijk2_ref, valid2_ref = oracle.kat_voxel(og2, border)
+    assert np.array_equal(kept2, valid2_ref)
+    assert np.array_equal(ijk2[valid2_ref == 1], ijk2_ref[valid2_ref == 1])
+    fus.close(); fus2.close()
+
+
+def test_kat_pca_normal(pcf, oracle):
+    """a10: float covariance in neighbour order + eigen33, both root branches."""
+    rng = np.random.default_rng(1)
+    fus = pcf.Fusion((-0.25, 0.25) * 3, 0.005)
+    res = np.float64(np.float32(0.001))
+    for trial in range(300):
+        base = rng.integers(10, 400, 3)
+        if trial % 3 == 0:      # perfect axis-aligned plane -> computeRoots2 branch
+            occ = np.zeros((5, 5, 5), bool); occ[:, :, 2] = True
+        elif trial % 3 == 1:    # noisy tilted sheet -> trigonometric branch
+            i, j = np.meshgrid(np.arange(5), np.arange(5), indexing="ij")
+            k = np.clip(np.round(2 + 0.4 * (i - 2) - 0.3 * (j - 2) + rng.normal(0, 0.5, (5, 5))), 0, 4).astype(int)
+            occ = np.zeros((5, 5, 5), bool); occ[i, j, k] = True
+            occ |= rng.random((5, 5, 5)) < 0.1
+        else:
+            occ = rng.random((5, 5, 5)) < 0.4
+        idx = np.argwhere(occ)   # ascending (i, j, k) = the reference's d order
+        if len(idx) < 21:
+            continue
+        centres = (-0.25 + res * (base + idx) + res / 2.0).astype(np.float32)
+        _, want, _ = oracle.kat_normal(centres)
+        got = fus.kat_normal(centres)
+        assert bits_equal(got, want), (trial, got, want)
+    fus.close()
+
+
+def test_kat_cylinder_score(pcf, oracle):
+    """a8/a11: projection, 1 mm test and the Welford recurrences, sequential order."""
+    rng = np.random.default_rng(2)
+    fus = pcf.Fusion((-0.25, 0.25) * 3, 0.005)
+    for trial in range(50):
+        c = rng.uniform(-0.2, 0.2, 3).astype(np.float32)
+        n = rng.normal(size=3); n = (n / np.linalg.norm(n)).astype(np.float32)
+        t = rng.uniform(-0.004, 0.004, 400)[:, None]
+        pts = (c + t * n + rng.normal(0, 0.0007, (400, 3))).astype(np.float32)
+        want = oracle.kat_score(pts, c, n)
+        got = fus.kat_score(pts, c, n)
+        assert got[4] == want[4] and got[4] > 0
+        for g, w in zip(got[:4], want[:4]):
+            assert bits_equal(np.asarray(g, np.float32), np.asarray(w, np.float32)), (trial, got, want)
+    fus.close()
+
+
+@pytest.mark.parametrize("update_every", [None, 1, 2])
+def test_replay_parity_small(pcf, oracle, small, update_every):
+    """End to end: frames -> update schedule -> extraction; grid state and output bit-exact."""
+    g = small.grid
+    og = oracle.OracleGrid(g.box, g.res)
+    fus = pcf.Fusion(g.box, g.res)
+    run_schedule(og, small, update_every)
+    run_schedule(fus, small, update_every)
+    assert fus.dims == og.dims
+    assert_same(fus.state(), og.state(), STATE_FIELDS, "state.")
+    want, got = og.download(), fus.extract()
+    assert len(want) > 1000
+    assert_result_parity(got, want, "result.")
+    fus.close()
+
+
+def test_device_batch_matches_host_frames(pcf, small):
+    """pcf_push_frames_device (one launch for the whole batch) == per-frame host pushes."""
+    import torch
+    g = small.grid
+    frames = [small.frame(i) for i in range(small.n_frames)]
+    a = pcf.Fusion(g.box, g.res)
+    for i, (pts, T) in enumerate(frames):
+        a.push_frame(pts, T, i)
+    a.update()
+    b = pcf.Fusion(g.box, g.res)
+    dev = torch.from_numpy(np.stack([f[0] for f in frames])).cuda()
+    b.push_frames_device(dev, len(frames), frames[0][0].shape[0], 4, np.stack([f[1] for f in frames]), 0)
+    b.update()
+    assert_same(b.extract(), a.extract(), RESULT_FIELDS)
+    assert_same(b.state(), a.state(), STATE_FIELDS)
+    a.close(); b.close()
+
+
+def test_stride3_and_clear_and_restart(pcf, oracle, small):
+    g = small.grid
+    og = oracle.OracleGrid(g.box, g.res)
+    fus = pcf.Fusion(g.box, g.res, started=False)
+    pts, T = small.frame(0)
+    assert fus.push_frame(pts, T, 0) == 1          # dropped while stopped (node.cpp:329)
+    fus.start()
+    for rep in range(2):                           # second round after clear must equal the first
+        for i in range(3):
+            pts, T = small.frame(i)
+            fus.push_frame(np.ascontiguousarray(pts[:, :3]), T, i)   # packed xyz
+            if rep == 0:
+                og.add_frame(pts, T)
+        fus.update()
+        if rep == 0:
+            og.update()
+            want = og.download()
+        assert_result_parity(fus.extract(), want)
+        fus.clear()
+        assert len(fus.extract()) == 0
+    fus.close()

@@ -1,0 +1,4 @@
+set -x
+nvidia-smi --query-gpu=name,memory.total --format=csv
+cd $GRAFT_REPO_ROOT
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -40
