@@ -46,7 +46,7 @@ class _Stats(C.Structure):
 
 ABI_SYMBOLS = [
     "pcf_default_config", "pcf_create", "pcf_destroy", "pcf_last_error", "pcf_dims", "pcf_start", "pcf_stop", "pcf_reset",
-    "pcf_push_frame", "pcf_push_frames_device", "pcf_sync", "pcf_update", "pcf_extract", "pcf_process", "pcf_write_result",
+    "pcf_push_frame", "pcf_push_frames_device", "pcf_sync", "pcf_count_kept", "pcf_update", "pcf_extract", "pcf_process", "pcf_write_result",
     "pcf_extract_hq", "pcf_clear", "pcf_dump_state", "pcf_get_stats", "pcf_reset_stats", "pcf_last_timings", "pcf_stream",
     "pcf_grid_buffer", "pcf_viewpoint_table", "pcf_log_compact", "pcf_log_replace", "pcf_kat_transform_voxel",
     "pcf_kat_normal", "pcf_kat_score",
@@ -77,6 +77,7 @@ def load_library():
         getattr(lib, name).argtypes = [vp]
     lib.pcf_push_frame.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32]
     lib.pcf_push_frames_device.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_uint32]
+    lib.pcf_count_kept.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.pcf_extract.argtypes = [vp, C.POINTER(_Result)]
     lib.pcf_extract_hq.argtypes = [vp, C.c_double, C.POINTER(_Result)]
     lib.pcf_process.argtypes = [vp, C.c_char_p, C.c_char_p]
@@ -208,6 +209,11 @@ class Fusion:
 
     def sync(self):
         self._ck(self.lib.pcf_sync(self.h))
+
+    def count_kept(self) -> int:
+        k = C.c_uint64()
+        self._ck(self.lib.pcf_count_kept(self.h, C.byref(k)))
+        return int(k.value)
 
     def update(self):
         self._ck(self.lib.pcf_update(self.h))

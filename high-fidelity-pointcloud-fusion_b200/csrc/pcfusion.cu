@@ -685,6 +685,25 @@ int pcf_sync(pcf_ctx* c) {
     return PCF_OK;
 }
 
+int pcf_count_kept(pcf_ctx* c, uint64_t* kept) {
+    if (!c || !kept) return PCF_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    uint32_t P = 0;
+    if (c->n_chunks) {
+        int rc = reserve(c, c->tmpB, (size_t)c->n_chunks * 4);
+        if (rc) return rc;
+        uint32_t* tot = (uint32_t*)c->total_dev.p;
+        if ((rc = scan_u32(c, c->chunk_count, (uint32_t*)c->tmpB.p, c->n_chunks, tot))) return rc;
+        if ((rc = read_total(c, tot, &P))) return rc;
+    } else {
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    c->stats.points_kept = P;
+    *kept = P;
+    return PCF_OK;
+}
+
 int pcf_update(pcf_ctx* c) {
     if (!c) return PCF_ERR_INVALID;
     CU(cudaSetDevice(c->device));

@@ -115,6 +115,9 @@ int pcf_push_frame(pcf_ctx* ctx, const float* pts_host, uint32_t n, uint32_t str
 int pcf_push_frames_device(pcf_ctx* ctx, const float* pts_dev, uint32_t n_frames, uint32_t n_per_frame,
                            uint32_t stride_floats, const double* poses, uint32_t first_frame_idx);
 int pcf_sync(pcf_ctx* ctx);     /* wait for all queued integration work */
+/* Drain, then read back how many points passed the clip + box test so far (the integration result summary:
+ * what the node prints as "Pointcloud N states updated..", node.cpp:297). */
+int pcf_count_kept(pcf_ctx* ctx, uint64_t* kept);
 
 /* updateThicknessVectors<N,K>(): neighbour scan, PCA normal, +-K walk registration.  OG.hpp:311-454,
  * called by the cleanGrid thread every 5 s (node.cpp:301-325); here the schedule is explicit (D4). */

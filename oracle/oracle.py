@@ -19,6 +19,7 @@ _LIBS = {
     "oracle": (os.path.join(_HERE, "_build", "liboracle.so"), "ora_"),
     "ref": (os.path.join(_HERE, "_ref", "libogref.so"), "ref_"),
     "ref_ordered": (os.path.join(_HERE, "_ref", "libogref_ordered.so"), "ref_"),
+    "ref_timing": (os.path.join(_HERE, "_ref", "libogref_timing.so"), "ref_"),
 }
 _loaded = {}
 

@@ -11,6 +11,7 @@
 //   D3  -DOGREF_ORDERED_KEYS swaps the two work lists for an ascending-order set (second build variant)
 #include <cstdlib>
 #include <new>
+#ifndef OGREF_STOCK_NEW
 #define OGREF_LOCAL __attribute__((visibility("hidden")))
 OGREF_LOCAL void* operator new(std::size_t n) { void* p = std::calloc(1, n ? n : 1); if (!p) throw std::bad_alloc(); return p; }
 OGREF_LOCAL void* operator new[](std::size_t n) { void* p = std::calloc(1, n ? n : 1); if (!p) throw std::bad_alloc(); return p; }
@@ -18,6 +19,7 @@ OGREF_LOCAL void operator delete(void* p) noexcept { std::free(p); }
 OGREF_LOCAL void operator delete[](void* p) noexcept { std::free(p); }
 OGREF_LOCAL void operator delete(void* p, std::size_t) noexcept { std::free(p); }
 OGREF_LOCAL void operator delete[](void* p, std::size_t) noexcept { std::free(p); }
+#endif  // OGREF_STOCK_NEW (timing build: the reference's own malloc behaviour, D1 unpinned)
 
 #include <cstdint>
 #include "utilities/OccupancyGrid.hpp"
