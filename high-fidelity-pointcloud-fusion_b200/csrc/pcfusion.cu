@@ -26,7 +26,7 @@ struct DevBuf {   // grow-only device allocation
 };
 
 constexpr int kRing = 4;           // staging slots for host frames
-constexpr uint32_t kMaxChunks = 1u << 21;   // slot index must fit 32 bits: 2^21 chunks * 2048
+constexpr uint32_t kMaxChunks = 1u << 24;   // slot index must fit 32 bits: 2^24 chunks * 256
 
 }  // namespace
 
@@ -64,10 +64,6 @@ struct pcf_ctx {
     size_t stage_cap[kRing] = {};
     cudaEvent_t ev_copied[kRing] = {}, ev_free[kRing] = {};
     int ring_pos = 0;
-    FrameDesc* desc_dev = nullptr;        // batch descriptors
-    FrameDesc* desc_host = nullptr;       // pinned
-    uint32_t desc_cap = 0;
-    cudaEvent_t ev_desc = nullptr;
 
     // scratch
     DevBuf scan1, scan2, tmpA, tmpB, tmpC, tmpD, hist, keysA, keysB, valsA, valsB, sorted, uv_cell, uv_off, nidx,
@@ -215,14 +211,14 @@ int read_total(pcf_ctx* c, const uint32_t* total_dev, uint32_t* out) {
 
 int ensure_log(pcf_ctx* c, uint32_t need_chunks) {
     if (need_chunks <= c->cap_chunks) return PCF_OK;
-    if (need_chunks > kMaxChunks) return fail(c, PCF_ERR_CAPACITY, "point log limit reached (%u chunks of %d input points)", kMaxChunks, kChunk);
+    if (need_chunks > kMaxChunks) return fail(c, PCF_ERR_CAPACITY, "point log limit reached (%u chunks of %d input points)", kMaxChunks, kWChunk);
     uint32_t cap = std::max<uint32_t>(need_chunks, std::min<uint64_t>((uint64_t)c->cap_chunks * 2, kMaxChunks));
     float4* nl = nullptr;
     uint32_t* nc = nullptr;
-    CU(cudaMalloc(&nl, (size_t)cap * kChunk * sizeof(float4)));
+    CU(cudaMalloc(&nl, (size_t)cap * kWChunk * sizeof(float4)));
     CU(cudaMalloc(&nc, (size_t)cap * 4));
     if (c->n_chunks) {
-        CU(cudaMemcpyAsync(nl, c->log, (size_t)c->n_chunks * kChunk * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(nl, c->log, (size_t)c->n_chunks * kWChunk * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
         CU(cudaMemcpyAsync(nc, c->chunk_count, (size_t)c->n_chunks * 4, cudaMemcpyDeviceToDevice, c->stream));
     }
     CU(cudaStreamSynchronize(c->stream));
@@ -240,8 +236,7 @@ int build_occupancy(pcf_ctx* c) {
     int rc = reserve(c, c->tmpA, (size_t)c->n_words * 4);
     if (rc) return rc;
     uint32_t* pop = (uint32_t*)c->tmpA.p;
-    uint32_t blocks = std::min<uint32_t>(div_up(c->n_words * 32, kBlock), 148 * 16);
-    LAUNCH(c, k_cells_to_bits, blocks, kBlock, c->first_frame, c->g.cells, c->occ_bits, pop, c->n_words);
+    LAUNCH(c, k_cells_to_bits, div_up(c->n_words, kBlock), kBlock, c->first_frame, c->g.cells, c->occ_bits, pop, c->n_words);
     uint32_t* tot = (uint32_t*)c->total_dev.p;
     rc = scan_u32(c, pop, c->occ_rank, c->n_words, tot);
     if (rc) return rc;
@@ -271,15 +266,27 @@ int flush_holders(pcf_ctx* c) {
     return PCF_OK;
 }
 
-template <bool BATCH>
-int launch_ingest(pcf_ctx* c, uint32_t stride, dim3 grid, const FrameDesc* descs, const FrameDesc& single) {
-    if (stride == 4)
-        LAUNCH(c, (k_ingest<4, BATCH>), grid, kBlock, descs, single, stride, c->g, c->first_frame, c->log, c->chunk_count, c->vp_table);
-    else if (stride == 3)
-        LAUNCH(c, (k_ingest<3, BATCH>), grid, kBlock, descs, single, stride, c->g, c->first_frame, c->log, c->chunk_count, c->vp_table);
-    else
-        LAUNCH(c, (k_ingest<0, BATCH>), grid, kBlock, descs, single, stride, c->g, c->first_frame, c->log, c->chunk_count, c->vp_table);
+// one launch over `nf` equally sized clouds resident in device memory
+int launch_ingest(pcf_ctx* c, const float* pts_dev, uint64_t frame_stride, uint32_t n, uint32_t nf, uint32_t stride,
+                  const double* poses, uint32_t first_frame_idx) {
+    static thread_local IngestBatch b;     // 12 KB of kernel parameters
+    uint32_t chunks = div_up(n, kWChunk);
+    b.pts = pts_dev;
+    b.frame_stride = frame_stride;
+    b.n = n;
+    b.n_frames = nf;
+    b.first_frame_idx = first_frame_idx;
+    b.chunk_base = c->n_chunks;
+    b.chunks_per_frame = chunks;
+    b.pad = 0;
+    for (uint32_t f = 0; f < nf; f++)
+        for (int i = 0; i < 12; i++) b.T[f][i] = poses[(size_t)f * 16 + i];
+    dim3 grid(div_up(chunks, kWarps), nf, 1);
+    if (stride == 4) LAUNCH(c, k_ingest<4>, grid, kBlock, b, stride, c->g, c->first_frame, c->log, c->chunk_count, c->vp_table);
+    else if (stride == 3) LAUNCH(c, k_ingest<3>, grid, kBlock, b, stride, c->g, c->first_frame, c->log, c->chunk_count, c->vp_table);
+    else LAUNCH(c, k_ingest<0>, grid, kBlock, b, stride, c->g, c->first_frame, c->log, c->chunk_count, c->vp_table);
     CU(cudaGetLastError());
+    c->n_chunks += chunks * nf;
     return PCF_OK;
 }
 
@@ -289,21 +296,12 @@ int check_frame_idx(pcf_ctx* c, uint32_t first, uint32_t count) {
     return PCF_OK;
 }
 
-void fill_desc(FrameDesc& d, const float* dev_pts, uint32_t n, uint32_t frame_idx, uint32_t chunk_base, const double* pose) {
-    d.pts = dev_pts;
-    d.n = n;
-    d.frame_idx = frame_idx;
-    d.chunk_base = chunk_base;
-    d.pad = 0;
-    for (int i = 0; i < 12; i++) d.T[i] = pose[i];
-}
-
 // (cell, slot) pairs sorted by cell, stable in slot order; then the sorted point stream and per-voxel CSR
 int prepare_sorted(pcf_ctx* c) {
     if (c->sorted_valid) return PCF_OK;
-    int rc = flush_holders(c);
-    if (rc) return rc;
-    rc = build_occupancy(c);
+    // (pending holder registrations are not needed here: they only matter once a later frame lands, and
+    //  pcf_push_* flushes them before that frame is integrated)
+    int rc = build_occupancy(c);
     if (rc) return rc;
     uint32_t* tot = (uint32_t*)c->total_dev.p;
     // number of kept points
@@ -342,14 +340,15 @@ int prepare_sorted(pcf_ctx* c) {
     int per = (bits + passes - 1) / passes;
     uint32_t mask = (1u << per) - 1;
     uint32_t tiles_later = div_up(P, kChunk);
-    if ((rc = reserve(c, c->hist, (size_t)256 * std::max(c->n_chunks, tiles_later) * 4))) return rc;
+    uint32_t tiles_log = div_up(c->n_chunks, kWarps);
+    if ((rc = reserve(c, c->hist, (size_t)256 * std::max(tiles_log, tiles_later) * 4))) return rc;
     uint32_t* hist = (uint32_t*)c->hist.p;
     uint32_t *kin = nullptr, *vin = nullptr, *kout = (uint32_t*)c->keysA.p, *vout = (uint32_t*)c->valsA.p;
     for (int p = 0; p < passes; p++) {
         SortSrc src{};
-        src.log = c->log; src.chunk_count = c->chunk_count; src.keys = kin; src.vals = vin; src.n = P;
+        src.log = c->log; src.chunk_count = c->chunk_count; src.keys = kin; src.vals = vin; src.n = P; src.n_chunks = c->n_chunks;
         uint32_t shift = (uint32_t)(p * per);
-        uint32_t nt = p == 0 ? c->n_chunks : tiles_later;
+        uint32_t nt = p == 0 ? tiles_log : tiles_later;
         if (p == 0) LAUNCH(c, k_sort_hist<true>, nt, kBlock, src, nt, shift, mask, hist);
         else LAUNCH(c, k_sort_hist<false>, nt, kBlock, src, nt, shift, mask, hist);
         rc = scan_u32(c, hist, hist, (uint64_t)256 * nt, nullptr);
@@ -462,18 +461,17 @@ void destroy_impl(pcf_ctx* c) {
                       &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->sorted, &c->uv_cell, &c->uv_off, &c->nidx, &c->sc_a, &c->sc_b,
                       &c->sc_c, &c->flags, &c->slots, &c->cand, &c->res_dev, &c->total_dev};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
-    void* raw[] = {c->first_frame, c->holder, c->nrm_bits, c->occ_bits, c->occ_rank, c->vp_table, c->log, c->chunk_count, c->desc_dev};
+    void* raw[] = {c->first_frame, c->holder, c->nrm_bits, c->occ_bits, c->occ_rank, c->vp_table, c->log, c->chunk_count};
     for (void* p : raw) if (p) cudaFree(p);
     for (int i = 0; i < kRing; i++) {
         if (c->stage[i]) cudaFree(c->stage[i]);
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
     }
-    if (c->desc_host) cudaFreeHost(c->desc_host);
     if (c->total_host) cudaFreeHost(c->total_host);
     if (c->res_host) cudaFreeHost(c->res_host);
     if (c->st_host) cudaFreeHost(c->st_host);
-    cudaEvent_t evs[] = {c->ev_desc, c->ev_a, c->ev_b, c->ev_c};
+    cudaEvent_t evs[] = {c->ev_a, c->ev_b, c->ev_c};
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -554,14 +552,13 @@ int pcf_create(const pcf_config* cfg, pcf_ctx** out) {
         CUC(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
     }
-    CUC(cudaEventCreateWithFlags(&c->ev_desc, cudaEventDisableTiming));
     CUC(cudaEventCreate(&c->ev_a));
     CUC(cudaEventCreate(&c->ev_b));
     CUC(cudaEventCreate(&c->ev_c));
     if (reserve(c, c->total_dev, 64)) return bail(PCF_ERR_CUDA);
     if (reset_grid_state(c)) return bail(PCF_ERR_CUDA);
     uint64_t hint = cfg->log_capacity_hint ? cfg->log_capacity_hint : (uint64_t)64 * 307200;
-    if (ensure_log(c, std::min<uint64_t>(div_up(hint, kChunk) + 1, kMaxChunks))) return bail(PCF_ERR_CUDA);
+    if (ensure_log(c, std::min<uint64_t>(div_up(hint, kWChunk) + 8, kMaxChunks))) return bail(PCF_ERR_CUDA);
     CUC(cudaStreamSynchronize(c->stream));
 #undef CUC
     *out = c;
@@ -596,7 +593,8 @@ int pcf_push_frame(pcf_ctx* c, const float* pts_host, uint32_t n, uint32_t strid
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
     if ((rc = flush_holders(c))) return rc;
-    uint32_t chunks = div_up(n, kChunk);
+    uint32_t chunks = div_up(n, kWChunk);
+    if ((uint64_t)c->n_chunks + chunks > kMaxChunks) return fail(c, PCF_ERR_CAPACITY, "point log limit reached");
     if ((rc = ensure_log(c, c->n_chunks + chunks))) return rc;
     int s = c->ring_pos;
     c->ring_pos = (c->ring_pos + 1) % kRing;
@@ -613,14 +611,11 @@ int pcf_push_frame(pcf_ctx* c, const float* pts_host, uint32_t n, uint32_t strid
     if (bytes) CU(cudaMemcpyAsync(c->stage[s], pts_host, bytes, cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaEventRecord(c->ev_copied[s], c->copy_stream));
     CU(cudaStreamWaitEvent(c->stream, c->ev_copied[s], 0));
-    FrameDesc d;
-    fill_desc(d, c->stage[s], n, frame_idx, c->n_chunks, pose);
     if (chunks) {
-        rc = launch_ingest<false>(c, stride, dim3(chunks, 1, 1), nullptr, d);
+        rc = launch_ingest(c, c->stage[s], 0, n, 1, stride, pose, frame_idx);
         if (rc) return rc;
     }
     CU(cudaEventRecord(c->ev_free[s], c->stream));
-    c->n_chunks += chunks;
     c->last_frame_idx = frame_idx;
     c->occ_dirty = true;
     c->sorted_valid = false;
@@ -640,40 +635,22 @@ int pcf_push_frames_device(pcf_ctx* c, const float* pts_dev, uint32_t n_frames, 
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
     if ((rc = flush_holders(c))) return rc;
-    uint32_t chunks = div_up(n_per_frame, kChunk);
+    uint32_t chunks = div_up(n_per_frame, kWChunk);
     if ((uint64_t)c->n_chunks + (uint64_t)chunks * n_frames > kMaxChunks) return fail(c, PCF_ERR_CAPACITY, "point log limit reached");
     if ((rc = ensure_log(c, c->n_chunks + chunks * n_frames))) return rc;
-    if (n_frames > c->desc_cap) {
-        CU(cudaStreamSynchronize(c->stream));
-        if (c->desc_dev) CU(cudaFree(c->desc_dev));
-        if (c->desc_host) CU(cudaFreeHost(c->desc_host));
-        c->desc_dev = nullptr; c->desc_host = nullptr;
-        uint32_t cap = std::max<uint32_t>(n_frames, 256);
-        CU(cudaMalloc(&c->desc_dev, (size_t)cap * sizeof(FrameDesc)));
-        CU(cudaMallocHost(&c->desc_host, (size_t)cap * sizeof(FrameDesc)));
-        c->desc_cap = cap;
-        CU(cudaEventRecord(c->ev_desc, c->stream));
-    }
-    CU(cudaEventSynchronize(c->ev_desc));   // previous batch has consumed the pinned descriptors
-    for (uint32_t f = 0; f < n_frames; f++) {
-        const double* pose = poses + (size_t)f * 16;
-        fill_desc(c->desc_host[f], pts_dev + (size_t)f * n_per_frame * stride, n_per_frame, first_frame_idx + f,
-                  c->n_chunks + f * chunks, pose);
-    }
-    CU(cudaMemcpyAsync(c->desc_dev, c->desc_host, (size_t)n_frames * sizeof(FrameDesc), cudaMemcpyHostToDevice, c->stream));
     if (chunks) {
-        FrameDesc dummy{};
-        rc = launch_ingest<true>(c, stride, dim3(chunks, n_frames, 1), c->desc_dev, dummy);
-        if (rc) return rc;
+        for (uint32_t f0 = 0; f0 < n_frames; f0 += kMaxBatch) {
+            uint32_t nf = std::min<uint32_t>(kMaxBatch, n_frames - f0);
+            rc = launch_ingest(c, pts_dev + (size_t)f0 * n_per_frame * stride, (uint64_t)n_per_frame * stride, n_per_frame, nf, stride,
+                               poses + (size_t)f0 * 16, first_frame_idx + f0);
+            if (rc) return rc;
+        }
     }
-    CU(cudaEventRecord(c->ev_desc, c->stream));
-    c->n_chunks += chunks * n_frames;
     c->last_frame_idx = (int64_t)first_frame_idx + n_frames - 1;
     c->occ_dirty = true;
     c->sorted_valid = false;
     c->stats.frames_pushed += n_frames;
     c->stats.points_offered += (uint64_t)n_frames * n_per_frame;
-    c->stats.h2d_bytes += (size_t)n_frames * sizeof(FrameDesc);
     return PCF_OK;
 }
 
@@ -711,7 +688,7 @@ int pcf_update(pcf_ctx* c) {
     int rc = flush_holders(c);
     if (rc) return rc;
     if ((rc = build_occupancy(c))) return rc;
-    uint32_t mark = c->n_chunks * (uint32_t)kChunk;   // n_chunks <= 2^21 -> fits (2^32 wraps only at the hard limit)
+    uint32_t mark = c->n_chunks * (uint32_t)kWChunk;   // n_chunks <= 2^24 -> fits (2^32 wraps only at the hard limit)
     if (c->n_chunks >= kMaxChunks) mark = 0xFFFFFFFFu;
     c->marks.push_back(mark);
     c->stats.update_passes++;
@@ -877,8 +854,8 @@ int pcf_kat_transform_voxel(pcf_ctx* c, const float* pts_host, uint32_t n, uint3
     CU(cudaMalloc(&d_ijk, (size_t)n * 12));
     CU(cudaMalloc(&d_k, (size_t)n));
     CU(cudaMemcpyAsync(d_in, pts_host, (size_t)n * stride * 4, cudaMemcpyHostToDevice, c->stream));
-    FrameDesc fd;
-    fill_desc(fd, d_in, n, 0, 0, pose);
+    PoseParam fd;
+    for (int i = 0; i < 12; i++) fd.T[i] = pose[i];
     LAUNCH(c, k_kat_transform_voxel, div_up(n, 256), 256, d_in, n, stride, fd, c->g, d_w, d_ijk, d_k);
     CU(cudaMemcpyAsync(world_xyz, d_w, (size_t)n * 12, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(ijk, d_ijk, (size_t)n * 12, cudaMemcpyDeviceToHost, c->stream));
