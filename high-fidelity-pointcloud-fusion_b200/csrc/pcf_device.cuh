@@ -14,7 +14,7 @@
 
 namespace pcf {
 
-constexpr uint32_t kEmpty = 0xFFFFFFFFu;   // first_frame value of an unoccupied cell
+constexpr uint32_t kEmpty = 0x7FFFFFFFu;   // first_frame value of an unoccupied cell (INT32_MAX: a signed min-reduce across GPUs works too)
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 
 // Everything a kernel needs to know about the grid.  Passed by value (fits the 4 KB param space).

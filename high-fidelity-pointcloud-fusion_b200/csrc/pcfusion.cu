@@ -292,7 +292,7 @@ int launch_ingest(pcf_ctx* c, const float* pts_dev, uint64_t frame_stride, uint3
 
 int check_frame_idx(pcf_ctx* c, uint32_t first, uint32_t count) {
     if ((int64_t)first <= c->last_frame_idx) return fail(c, PCF_ERR_INVALID, "frame_idx %u does not increase (last %lld)", first, (long long)c->last_frame_idx);
-    if ((uint64_t)first + count > c->cfg.max_frames) return fail(c, PCF_ERR_CAPACITY, "frame_idx %u exceeds max_frames %u", first + count - 1, c->cfg.max_frames);
+    if ((uint64_t)first + count > c->cfg.max_frames || (uint64_t)first + count >= kEmpty) return fail(c, PCF_ERR_CAPACITY, "frame_idx %u exceeds max_frames %u", first + count - 1, c->cfg.max_frames);
     return PCF_OK;
 }
 
@@ -479,7 +479,7 @@ void destroy_impl(pcf_ctx* c) {
 }
 
 int reset_grid_state(pcf_ctx* c) {
-    CU(cudaMemsetAsync(c->first_frame, 0xFF, c->g.cells * 4, c->stream));
+    LAUNCH(c, k_fill_u32, 148 * 8, 512, c->first_frame, c->g.cells, kEmpty);
     CU(cudaMemsetAsync(c->nrm_bits, 0, (c->n_words + 2) * 4, c->stream));
     CU(cudaMemsetAsync(c->occ_bits, 0, (c->n_words + 2) * 4, c->stream));
     CU(cudaMemsetAsync(c->vp_table, 0, (size_t)c->cfg.max_frames * sizeof(float4), c->stream));
