@@ -210,7 +210,19 @@ def run_b200(args):
             nb = min(BATCH, N_FRAMES - b)
             fus.push_frames_device(dev_frames[b], nb, npf, 4, poses[b:b + nb], first + b)
 
+    sh = None
+    if world > 1:
+        import importlib
+        sh = importlib.import_module("high-fidelity-pointcloud-fusion_b200.sharded")
+
     def process_and_clear(keep=None):
+        if world > 1:     # process() across ranks: grid MIN-reduce + viewpoint SUM + log all-gather over NCCL, then slab work
+            _, full, tm = sh.merge_and_extract(fus)
+            fus.clear()
+            if keep is not None:
+                keep.append({"update_ms": tm["exchange_ms"], "extract_device_ms": tm["slab_process_ms"], "extract_d2h_ms": 0.0,
+                             "voxels": len(full) if full is not None else 0})
+            return
         fus.update()
         t = fus.timings()
         n = fus.extract_raw()
@@ -305,7 +317,9 @@ def run_b200(args):
             "config": {"workload": WORKLOAD, "frames_per_gpu": N_FRAMES, "points_per_frame": npf, "batch_frames_per_launch": BATCH,
                        "l2": "inputs (983 MB per step) larger than the 126 MB L2; no flush needed", "sharding": f"frames x{world}"},
             "process_ms": statistics.mean(p["update_ms"] + p["extract_device_ms"] + p["extract_d2h_ms"] for p in proc),
-            "process_detail": {k: statistics.mean(p[k] for p in proc) for k in ("update_ms", "extract_device_ms", "extract_d2h_ms", "voxels")},
+            "process_detail": dict({k: statistics.mean(p[k] for p in proc) for k in ("update_ms", "extract_device_ms", "extract_d2h_ms", "voxels")},
+                                   note=("update_ms = NCCL exchange (grid min-reduce, viewpoint sum, log all-gather); extract_device_ms = "
+                                         "slab update+extract incl. D2H; rank 0's view") if world > 1 else "single GPU"),
             "step_wall_ms": 1e3 * t_wall / args.steps,
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(points_per_step * 16),
                     "d2h_bytes_per_step": 4, "process_wall_ms": statistics.mean(e2e_proc)},

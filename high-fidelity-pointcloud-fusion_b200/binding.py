@@ -48,7 +48,7 @@ ABI_SYMBOLS = [
     "pcf_default_config", "pcf_create", "pcf_destroy", "pcf_last_error", "pcf_dims", "pcf_start", "pcf_stop", "pcf_reset",
     "pcf_push_frame", "pcf_push_frames_device", "pcf_sync", "pcf_count_kept", "pcf_update", "pcf_extract", "pcf_process", "pcf_write_result",
     "pcf_extract_hq", "pcf_clear", "pcf_dump_state", "pcf_get_stats", "pcf_reset_stats", "pcf_last_timings", "pcf_stream",
-    "pcf_grid_buffer", "pcf_viewpoint_table", "pcf_log_compact", "pcf_log_replace", "pcf_kat_transform_voxel",
+    "pcf_grid_buffer", "pcf_viewpoint_table", "pcf_log_compact", "pcf_log_replace", "pcf_set_slab", "pcf_plane_counts", "pcf_kat_transform_voxel",
     "pcf_kat_normal", "pcf_kat_score",
 ]
 
@@ -91,6 +91,8 @@ def load_library():
     lib.pcf_viewpoint_table.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint32)]
     lib.pcf_log_compact.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
     lib.pcf_log_replace.argtypes = [vp, vp, C.c_uint64]
+    lib.pcf_set_slab.argtypes = [vp, C.c_int32, C.c_int32]
+    lib.pcf_plane_counts.argtypes = [vp, vp]
     lib.pcf_kat_transform_voxel.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
     lib.pcf_kat_normal.argtypes = [vp, vp, C.c_uint32, vp]
     lib.pcf_kat_score.argtypes = [vp, vp, C.c_uint32, vp, vp, vp, vp, vp, vp, vp]
@@ -165,6 +167,7 @@ class Fusion:
         if rc != 0:
             raise PcfError(rc, self.lib.pcf_last_error(None).decode())
         self.h = h
+        self.device_index = device
         d = (C.c_int32 * 3)()
         self.lib.pcf_dims(self.h, C.byref(d))
         self.dims = tuple(d)
@@ -270,6 +273,22 @@ class Fusion:
         p, n = C.c_void_p(), C.c_uint32()
         self._ck(self.lib.pcf_viewpoint_table(self.h, C.byref(p), C.byref(n)))
         return p.value, int(n.value)
+
+    def log_compact(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(self.lib.pcf_log_compact(self.h, C.byref(p), C.byref(n)))
+        return p.value, int(n.value)
+
+    def log_replace(self, log_dev, n_points):
+        self._ck(self.lib.pcf_log_replace(self.h, _ptr(log_dev), n_points))
+
+    def set_slab(self, x_lo, x_hi):
+        self._ck(self.lib.pcf_set_slab(self.h, x_lo, x_hi))
+
+    def plane_counts(self):
+        out = np.zeros(self.dims[0] + 2, np.uint32)
+        self._ck(self.lib.pcf_plane_counts(self.h, out.ctypes.data))
+        return out
 
     # ---- known-answer hooks ----
     def kat_transform_voxel(self, pts, pose):

@@ -58,6 +58,8 @@ struct pcf_ctx {
     std::vector<uint32_t> marks;                       // log slot cursor at each update pass
     std::vector<std::pair<uint32_t, uint32_t>> pending_holder;   // [begin,end) normal records per pass not yet registered
     int64_t last_frame_idx = -1;
+    int32_t slab_lo = 0, slab_hi = -1;               // x-range owned by this context; hi < 0 = whole grid
+    DevBuf dense_log;
 
     // staging for host frames
     float* stage[kRing] = {};
@@ -459,7 +461,7 @@ void destroy_impl(pcf_ctx* c) {
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     DevBuf* bufs[] = {&c->n_cell, &c->n_nrm, &c->n_mark, &c->scan1, &c->scan2, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->hist,
                       &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->sorted, &c->uv_cell, &c->uv_off, &c->nidx, &c->sc_a, &c->sc_b,
-                      &c->sc_c, &c->flags, &c->slots, &c->cand, &c->res_dev, &c->total_dev};
+                      &c->sc_c, &c->flags, &c->slots, &c->cand, &c->res_dev, &c->total_dev, &c->dense_log};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     void* raw[] = {c->first_frame, c->holder, c->nrm_bits, c->occ_bits, c->occ_rank, c->vp_table, c->log, c->chunk_count};
     for (void* p : raw) if (p) cudaFree(p);
@@ -493,6 +495,8 @@ int reset_grid_state(pcf_ctx* c) {
     c->occ_dirty = true;
     c->sorted_valid = false;
     c->last_frame_idx = -1;
+    c->slab_lo = 0;
+    c->slab_hi = -1;
     return PCF_OK;
 }
 
@@ -699,7 +703,10 @@ int pcf_update(pcf_ctx* c) {
         if ((rc = reserve(c, c->tmpB, (size_t)c->n_words * 4))) return rc;
         uint32_t* cnt = (uint32_t*)c->tmpA.p;
         uint32_t* off = (uint32_t*)c->tmpB.p;
-        LAUNCH(c, k_cand_count, div_up(c->n_words, kBlock), kBlock, c->occ_bits, c->nrm_bits, c->n_words, cnt);
+        const uint64_t plane = (uint64_t)c->g.n1[1] * c->g.n1[2];
+        const uint64_t cell_lo = c->slab_hi < 0 ? 0 : (uint64_t)c->slab_lo * plane;
+        const uint64_t cell_hi = c->slab_hi < 0 ? c->g.cells : std::min<uint64_t>(c->g.cells, (uint64_t)c->slab_hi * plane);
+        LAUNCH(c, k_cand_count, div_up(c->n_words, kBlock), kBlock, c->occ_bits, c->nrm_bits, c->n_words, cell_lo, cell_hi, cnt);
         if ((rc = scan_u32(c, cnt, off, c->n_words, tot))) return rc;
         if ((rc = read_total(c, tot, &n_cand))) return rc;
         if (n_cand) {
@@ -710,7 +717,7 @@ int pcf_update(pcf_ctx* c) {
             float4* tnrm = (float4*)c->tmpC.p;
             uint32_t* flag = (uint32_t*)c->tmpD.p;
             uint32_t* foff = flag + n_cand;
-            LAUNCH(c, k_cand_list, div_up(c->n_words, kBlock), kBlock, c->occ_bits, c->nrm_bits, c->n_words, off, cand);
+            LAUNCH(c, k_cand_list, div_up(c->n_words, kBlock), kBlock, c->occ_bits, c->nrm_bits, c->n_words, cell_lo, cell_hi, off, cand);
             LAUNCH(c, k_normals, div_up(n_cand, kBlock), kBlock, cand, n_cand, c->g, c->occ_bits, c->first_frame, c->vp_table, tnrm, flag);
             if ((rc = scan_u32(c, flag, foff, n_cand, tot))) return rc;
             uint32_t n_new = 0;
@@ -772,6 +779,7 @@ int pcf_process(pcf_ctx* c, const char* cloud_path, const char* meta_path) {
 int pcf_dump_state(pcf_ctx* c, pcf_state* out) {
     if (!c || !out) return PCF_ERR_INVALID;
     memset(out, 0, sizeof *out);
+    if (c->slab_hi >= 0) return fail(c, PCF_ERR_INVALID, "pcf_dump_state needs the whole grid (an x-slab is set)");
     CU(cudaSetDevice(c->device));
     int rc = run_scoring(c);
     if (rc) return rc;
@@ -837,10 +845,95 @@ int pcf_viewpoint_table(pcf_ctx* c, void** vp_dev, uint32_t* max_frames) {
     return PCF_OK;
 }
 int pcf_log_compact(pcf_ctx* c, void** log_dev, uint64_t* n_points) {
-    return c ? fail(c, PCF_ERR_INVALID, "pcf_log_compact: not implemented yet") : PCF_ERR_INVALID;
+    if (!c || !log_dev || !n_points) return PCF_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    *log_dev = nullptr;
+    *n_points = 0;
+    uint32_t P = 0;
+    if (c->n_chunks) {
+        int rc = reserve(c, c->tmpB, (size_t)c->n_chunks * 4);
+        if (rc) return rc;
+        uint32_t* off = (uint32_t*)c->tmpB.p;
+        uint32_t* tot = (uint32_t*)c->total_dev.p;
+        if ((rc = scan_u32(c, c->chunk_count, off, c->n_chunks, tot))) return rc;
+        if ((rc = read_total(c, tot, &P))) return rc;
+        if ((rc = reserve(c, c->dense_log, std::max<size_t>((size_t)P, 1) * sizeof(float4)))) return rc;
+        LAUNCH(c, k_log_compact, div_up(c->n_chunks, kWarps), kBlock, c->log, c->chunk_count, off, c->n_chunks, (float4*)c->dense_log.p);
+        CU(cudaGetLastError());
+    } else {
+        int rc = reserve(c, c->dense_log, sizeof(float4));
+        if (rc) return rc;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    *log_dev = c->dense_log.p;
+    *n_points = P;
+    return PCF_OK;
 }
+
+int pcf_set_slab(pcf_ctx* c, int32_t x_lo, int32_t x_hi) {
+    if (!c) return PCF_ERR_INVALID;
+    if (x_hi >= 0 && (x_lo < 0 || x_lo > x_hi || (uint32_t)x_hi > c->g.n1[0])) return fail(c, PCF_ERR_INVALID, "bad slab [%d,%d)", x_lo, x_hi);
+    c->slab_lo = x_lo;
+    c->slab_hi = x_hi;
+    return PCF_OK;
+}
+
 int pcf_log_replace(pcf_ctx* c, const void* log_dev, uint64_t n_points) {
-    return c ? fail(c, PCF_ERR_INVALID, "pcf_log_replace: not implemented yet") : PCF_ERR_INVALID;
+    if (!c || (!log_dev && n_points)) return PCF_ERR_INVALID;
+    if (n_points >= 0xFFFFFFFFull) return fail(c, PCF_ERR_CAPACITY, "merged log too large");
+    if (c->n_normals) return fail(c, PCF_ERR_INVALID, "pcf_log_replace after pcf_update: sharded merge of interleaved schedules is not supported");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    const float4* in = (const float4*)log_dev;
+    // keep the records of this context's x-slab plus the reach of the +-K walk (OG.hpp:403-405): walk_k cells
+    const uint64_t plane = (uint64_t)c->g.n1[1] * c->g.n1[2];
+    uint64_t cell_lo = 0, cell_hi = c->g.cells;
+    if (c->slab_hi >= 0) {
+        int64_t lo = (int64_t)c->slab_lo - c->g.walk_k, hi = (int64_t)c->slab_hi + c->g.walk_k;
+        cell_lo = (uint64_t)std::max<int64_t>(lo, 0) * plane;
+        cell_hi = std::min<uint64_t>(c->g.cells, (uint64_t)std::max<int64_t>(hi, 0) * plane);
+    }
+    uint32_t kept = 0;
+    int rc;
+    c->n_chunks = 0;
+    if (n_points) {
+        if ((rc = reserve(c, c->tmpC, (size_t)n_points * 4))) return rc;
+        if ((rc = reserve(c, c->tmpD, (size_t)n_points * 4))) return rc;
+        uint32_t* flag = (uint32_t*)c->tmpC.p;
+        uint32_t* pos = (uint32_t*)c->tmpD.p;
+        uint32_t* tot = (uint32_t*)c->total_dev.p;
+        LAUNCH(c, k_log_filter_flags, div_up(n_points, kBlock), kBlock, in, n_points, cell_lo, cell_hi, flag);
+        if ((rc = scan_u32(c, flag, pos, n_points, tot))) return rc;
+        if ((rc = read_total(c, tot, &kept))) return rc;
+        uint32_t chunks = div_up(kept, kWChunk);
+        if (chunks > kMaxChunks) return fail(c, PCF_ERR_CAPACITY, "point log limit reached");
+        if ((rc = ensure_log(c, std::max<uint32_t>(chunks, 1)))) return rc;
+        if (kept) {
+            LAUNCH(c, k_log_install, div_up(n_points, kBlock), kBlock, in, n_points, flag, pos, c->log);
+            LAUNCH(c, k_chunk_counts_dense, div_up(chunks, kBlock), kBlock, c->chunk_count, chunks, (uint64_t)kept);
+        }
+        CU(cudaGetLastError());
+        c->n_chunks = chunks;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    c->occ_dirty = true;
+    c->sorted_valid = false;
+    return PCF_OK;
+}
+
+int pcf_plane_counts(pcf_ctx* c, uint32_t* counts_host) {
+    if (!c || !counts_host) return PCF_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    int rc = build_occupancy(c);
+    if (rc) return rc;
+    uint32_t np = c->g.n1[0];
+    if ((rc = reserve(c, c->tmpA, ((size_t)np + 1) * 4))) return rc;
+    LAUNCH(c, k_plane_counts, div_up(np + 1, kBlock), kBlock, c->occ_bits, c->occ_rank, np, (uint64_t)c->g.n1[1] * c->g.n1[2], c->n_vox,
+           (uint32_t*)c->tmpA.p);
+    CU(cudaMemcpyAsync(counts_host, c->tmpA.p, ((size_t)np + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return PCF_OK;
 }
 
 // ---- known-answer hooks -------------------------------------------------------------------------------

@@ -148,7 +148,13 @@ void* pcf_stream(pcf_ctx* ctx);
 int pcf_grid_buffer(pcf_ctx* ctx, void** first_frame_dev, uint64_t* n_cells);    /* uint32 per cell, 0x7FFFFFFF = empty */
 int pcf_viewpoint_table(pcf_ctx* ctx, void** vp_dev, uint32_t* max_frames);       /* float4 per frame_idx, w=1 when set */
 int pcf_log_compact(pcf_ctx* ctx, void** log_dev, uint64_t* n_points);            /* float4 (x,y,z,cell) in arrival order */
-int pcf_log_replace(pcf_ctx* ctx, const void* log_dev, uint64_t n_points);        /* install a merged log (arrival order) */
+/* x-slab [x_lo, x_hi) of voxels this context normal-estimates, scores and extracts (x_hi < 0: whole grid).  The
+ * concatenation of the ranks' extractions in slab order is the reference's x-major order (OG.hpp:463-465). */
+int pcf_set_slab(pcf_ctx* ctx, int32_t x_lo, int32_t x_hi);
+/* Install a merged log (records of all ranks in arrival order); only the slab +- walk_k planes are kept. */
+int pcf_log_replace(pcf_ctx* ctx, const void* log_dev, uint64_t n_points);
+/* counts_host[x] = occupied voxels with plane index < x, x = 0 .. xdim+1 (for balanced slab boundaries). */
+int pcf_plane_counts(pcf_ctx* ctx, uint32_t* counts_host);
 
 /* ---- known-answer hooks: run ONE device function over an array (tests bit-compare with the oracle) ---- */
 int pcf_kat_transform_voxel(pcf_ctx* ctx, const float* pts_host, uint32_t n, uint32_t stride_floats,

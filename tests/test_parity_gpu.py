@@ -152,3 +152,26 @@ def test_stride3_and_clear_and_restart(pcf, oracle, small):
         fus.clear()
         assert len(fus.extract()) == 0
     fus.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_frame_sharded_merge_is_byte_identical(pcf, small, world):
+    """N ranks emulated as N contexts on one GPU; merged extraction == 1-rank extraction."""
+    import importlib
+    sh = importlib.import_module(pcf.__name__ + ".sharded")
+    g = small.grid
+    frames = [small.frame(i) for i in range(small.n_frames)]
+    one = pcf.Fusion(g.box, g.res)
+    for i, (pts, T) in enumerate(frames):
+        one.push_frame(pts, T, i)
+    one.update()
+    want = one.extract()
+    ranks = [pcf.Fusion(g.box, g.res) for _ in range(world)]
+    for r, f in enumerate(ranks):
+        lo, hi = sh.frame_block(len(frames), r, world)
+        for i in range(lo, hi):
+            f.push_frame(frames[i][0], frames[i][1], i)
+    got = sh.merge_and_extract_local(ranks)
+    assert_same(got, want, RESULT_FIELDS, f"sharded x{world}: ")
+    for f in ranks + [one]:
+        f.close()
