@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = "turntable200: 200 x 640x480 organized clouds, sphere r=0.15 m, 1 mm voxels, 0.5 m box, two elevation rings"
 N_FRAMES = 200
-BATCH = 100           # frames per ingest launch on the HBM-resident path (library limit: 128)
+BATCH = 200           # frames per ingest launch on the HBM-resident path (library limit: 256)
 CPU_SAMPLE_FRAMES = 20
 
 

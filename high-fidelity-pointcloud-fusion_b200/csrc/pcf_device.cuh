@@ -10,7 +10,11 @@
 #pragma once
 #include <cfloat>
 #include <cstdint>
+#include <cstring>
+#include <cmath>
 #include <cuda_runtime.h>
+
+#define PCF_HD __host__ __device__ __forceinline__
 
 namespace pcf {
 
@@ -36,72 +40,171 @@ struct GridParams {
 };
 
 struct V3 { float x, y, z; };
-__device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
-__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
-__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
-__device__ __forceinline__ V3 operator*(float s, V3 a) { return mk(s * a.x, s * a.y, s * a.z); }
-__device__ __forceinline__ V3 operator/(V3 a, float s) { return mk(a.x / s, a.y / s, a.z / s); }
+PCF_HD V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+PCF_HD V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+PCF_HD V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+PCF_HD V3 operator*(float s, V3 a) { return mk(s * a.x, s * a.y, s * a.z); }
+PCF_HD V3 operator/(V3 a, float s) { return mk(a.x / s, a.y / s, a.z / s); }
 // Eigen's 3-term reduction order: x0 + (x1 + x2)
-__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + (a.y * b.y + a.z * b.z); }
-__device__ __forceinline__ float sqnorm(V3 a) { return dot(a, a); }
-__device__ __forceinline__ V3 normalized(V3 a) {
+PCF_HD float dot(V3 a, V3 b) { return a.x * b.x + (a.y * b.y + a.z * b.z); }
+PCF_HD float sqnorm(V3 a) { return dot(a, a); }
+PCF_HD V3 normalized(V3 a) {
     float z = sqnorm(a);
     if (z > 0.0f) return a / sqrtf(z);
     return a;
 }
-__device__ __forceinline__ V3 cross(V3 a, V3 b) {
+PCF_HD V3 cross(V3 a, V3 b) {
     return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
-__device__ __forceinline__ bool finite3(V3 a) { return isfinite(a.x) && isfinite(a.y) && isfinite(a.z); }
+PCF_HD bool finite3(V3 a) { return isfinite(a.x) && isfinite(a.y) && isfinite(a.z); }
+
+// ---- exact conversions without the XU pipe ------------------------------------------------------------------
+// F2F / FRND / F2I run on the 16-lane XU pipe; at 15 of them per point the integration kernel was XU-bound
+// (ncu r01: pipe_xu 45 %, fp64 19 %).  The three helpers below produce bit-identical results with integer and
+// FP64-pipe instructions only; values outside their fast range take the hardware conversion (rare branch).
+PCF_HD uint32_t d_hi(double d) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__double2hiint(d);
+#else
+    uint64_t u; memcpy(&u, &d, 8); return (uint32_t)(u >> 32);
+#endif
+}
+PCF_HD uint32_t d_lo(double d) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__double2loint(d);
+#else
+    uint64_t u; memcpy(&u, &d, 8); return (uint32_t)u;
+#endif
+}
+PCF_HD double mk_double(uint32_t hi, uint32_t lo) {
+#ifdef __CUDA_ARCH__
+    return __hiloint2double((int)hi, (int)lo);
+#else
+    uint64_t u = ((uint64_t)hi << 32) | lo; double d; memcpy(&d, &u, 8); return d;
+#endif
+}
+PCF_HD uint32_t f_bits(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+PCF_HD float bits_f(uint32_t u) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
+// double(f), exact.  Normal floats: re-bias the exponent (+896) and shift the mantissa by 3 bits.
+PCF_HD double f2d_exact(float f) {
+    uint32_t b = f_bits(f);
+    uint32_t e = b & 0x7f800000u;
+    if (e == 0u || e == 0x7f800000u) return (double)f;        // zero, denormal, inf, NaN
+    return mk_double((b & 0x80000000u) | (((b & 0x7fffffffu) >> 3) + 0x38000000u), b << 29);
+}
+
+// f = float(d) (round to nearest even) and r = double(f).  For |d| in [2^-126, 2^127): adding M = sign(d)*2^(e+29)
+// (e = exponent of d) makes the FP64 adder round d, to nearest even, to a multiple of 2^(e-23) -- the float
+// grid at that exponent (the sum's significand is 2^52 + k with k the float significand, so "even" agrees);
+// subtracting M again is exact.  The float bit pattern is then a pure re-packing of r.
+PCF_HD void narrow_f32(double d, double& r, float& f) {
+    uint32_t hi = d_hi(d);
+    uint32_t e = hi & 0x7ff00000u;
+    if (e - (897u << 20) <= ((1149u - 897u) << 20)) {
+        double M = mk_double((hi & 0xfff00000u) + (29u << 20), 0u);
+        r = (d + M) - M;
+        uint32_t rh = d_hi(r), rl = d_lo(r);
+        uint32_t m = (rh & 0x7fffffffu) - 0x38000000u;
+        f = bits_f((rh & 0x80000000u) | (m << 3) | (rl >> 29));
+    } else {
+        f = (float)d;
+        r = (double)f;
+    }
+}
 
 // ---- rigid transform: out = float(T(r,0)*x + T(r,1)*y + T(r,2)*z + T(r,3)), double, left to right ----------
-__device__ __forceinline__ V3 transform_point(const double* __restrict__ T, float x, float y, float z) {
-    double dx = (double)x, dy = (double)y, dz = (double)z;
+// (PCL transformPointCloud(Affine3d), node.cpp:289).  wd receives double(out) for the voxel index.
+template <bool HW = false>
+PCF_HD V3 transform_point(const double* __restrict__ T, float x, float y, float z, double wd[3]) {
     V3 o;
-    o.x = (float)(T[0] * dx + T[1] * dy + T[2] * dz + T[3]);
-    o.y = (float)(T[4] * dx + T[5] * dy + T[6] * dz + T[7]);
-    o.z = (float)(T[8] * dx + T[9] * dy + T[10] * dz + T[11]);
+    if (HW) {      // hardware conversions (F2F on the XU pipe): the plain statement of the formula
+        double dx = (double)x, dy = (double)y, dz = (double)z;
+        o.x = (float)(T[0] * dx + T[1] * dy + T[2] * dz + T[3]);
+        o.y = (float)(T[4] * dx + T[5] * dy + T[6] * dz + T[7]);
+        o.z = (float)(T[8] * dx + T[9] * dy + T[10] * dz + T[11]);
+        wd[0] = (double)o.x; wd[1] = (double)o.y; wd[2] = (double)o.z;
+        return o;
+    }
+    double dx = f2d_exact(x), dy = f2d_exact(y), dz = f2d_exact(z);
+    narrow_f32(T[0] * dx + T[1] * dy + T[2] * dz + T[3], wd[0], o.x);
+    narrow_f32(T[4] * dx + T[5] * dy + T[6] * dz + T[7], wd[1], o.y);
+    narrow_f32(T[8] * dx + T[9] * dy + T[10] * dz + T[11], wd[2], o.z);
     return o;
 }
 
 // strict box test; the float thresholds make it identical to the reference's double compares, NaN fails (D11)
-__device__ __forceinline__ bool valid_point(const GridParams& g, V3 p) {
+PCF_HD bool valid_point(const GridParams& g, V3 p) {
     return p.x > g.lo[0] && p.x < g.hi[0] && p.y > g.lo[1] && p.y < g.hi[1] && p.z > g.lo[2] && p.z < g.hi[2];
 }
 
-// floor((double(p) - min) / res).  a * (1/res) is within 2 ulp of the true quotient; only when it lands
-// within 1e-6 of an integer can floor() of the correctly rounded quotient differ, and then we divide.
-__device__ __forceinline__ int voxel_axis(double a, double res, double inv_res) {
-    double q = a * inv_res;
-    double fq = floor(q);
-    double fr = q - fq;
-    if (fr < 1e-6 || fr > 1.0 - 1e-6) fq = floor(__ddiv_rn(a, res));
-    return (int)fq;
+// floor(a / res) for a point strictly inside the box (0 < a, a/res < 2^20), OG.hpp:633-635.
+// q = a * (1/res) is within 2 ulp of the true quotient.  One FP64 add exposes floor(q) and the distance to the
+// next cell border as integer fields; `near` asks the caller for voxel_axis_exact (kept out of line so that the
+// hot path stays branch-free and needs no FRND / F2I on the XU pipe).
+PCF_HD int voxel_axis_fast(double a, double inv_res, bool& near) {
+    // t in [2^32, 2^33): ulp(t) = 2^-20, so the significand holds rint(q * 2^20): integer part of q in bits 51..20,
+    // fraction in bits 19..0.  A non-zero fraction field proves q, and therefore the correctly rounded a / res
+    // (|q - a/res| < 2^-31), lies strictly inside (n, n + 1): floor is n.  Fraction field 0 (p = 2^-20): divide.
+    double t = a * inv_res + 4294967296.0;
+    uint32_t hi = d_hi(t), lo = d_lo(t);
+    near = (lo & 0xFFFFFu) == 0u;
+    return (int)((hi << 12) | (lo >> 20));
 }
-__device__ __forceinline__ void voxel_coords(const GridParams& g, V3 p, int& x, int& y, int& z) {
-    x = voxel_axis((double)p.x - g.min[0], g.res[0], g.inv_res[0]);
-    y = voxel_axis((double)p.y - g.min[1], g.res[1], g.inv_res[1]);
-    z = voxel_axis((double)p.z - g.min[2], g.res[2], g.inv_res[2]);
+PCF_HD int voxel_axis_exact(double a, double res) {
+#ifdef __CUDA_ARCH__
+    return (int)floor(__ddiv_rn(a, res));
+#else
+    return (int)floor(a / res);
+#endif
 }
-__device__ __forceinline__ bool valid_coord(const GridParams& g, int x, int y, int z) {
+PCF_HD int voxel_axis(double a, double res, double inv_res) {
+    bool near;
+    int i = voxel_axis_fast(a, inv_res, near);
+    if (near) i = voxel_axis_exact(a, res);
+    return i;
+}
+// pd = double(p) per axis (p passed valid_point)
+PCF_HD void voxel_coords_d(const GridParams& g, const double pd[3], int& x, int& y, int& z) {
+    x = voxel_axis(pd[0] - g.min[0], g.res[0], g.inv_res[0]);
+    y = voxel_axis(pd[1] - g.min[1], g.res[1], g.inv_res[1]);
+    z = voxel_axis(pd[2] - g.min[2], g.res[2], g.inv_res[2]);
+}
+PCF_HD void voxel_coords(const GridParams& g, V3 p, int& x, int& y, int& z) {
+    double pd[3] = {f2d_exact(p.x), f2d_exact(p.y), f2d_exact(p.z)};
+    voxel_coords_d(g, pd, x, y, z);
+}
+PCF_HD bool valid_coord(const GridParams& g, int x, int y, int z) {
     return x >= 0 && y >= 0 && z >= 0 && x < g.dim[0] && y < g.dim[1] && z < g.dim[2];
 }
-__device__ __forceinline__ uint32_t cell_index(const GridParams& g, int x, int y, int z) {
+PCF_HD uint32_t cell_index(const GridParams& g, int x, int y, int z) {
     return ((uint32_t)x * g.n1[1] + (uint32_t)y) * g.n1[2] + (uint32_t)z;
 }
-__device__ __forceinline__ void cell_coords(const GridParams& g, uint32_t cell, int& x, int& y, int& z) {
+PCF_HD void cell_coords(const GridParams& g, uint32_t cell, int& x, int& y, int& z) {
     uint32_t xy = cell / g.n1[2];
     z = (int)(cell - xy * g.n1[2]);
     x = (int)(xy / g.n1[1]);
     y = (int)(xy - (uint32_t)x * g.n1[1]);
 }
-__device__ __forceinline__ uint64_t hash_id(int x, int y, int z) {
+PCF_HD uint64_t hash_id(int x, int y, int z) {
     return ((uint64_t)x << 40) ^ ((uint64_t)y << 20) ^ (uint64_t)z;
 }
-__device__ __forceinline__ float center_axis(const GridParams& g, int axis, int i) {
+PCF_HD float center_axis(const GridParams& g, int axis, int i) {
     return (float)(g.min[axis] + g.res[axis] * (double)i + g.half_res[axis]);
 }
-__device__ __forceinline__ V3 voxel_center(const GridParams& g, int x, int y, int z) {
+PCF_HD V3 voxel_center(const GridParams& g, int x, int y, int z) {
     return mk(center_axis(g, 0, x), center_axis(g, 1, y), center_axis(g, 2, z));
 }
 
@@ -110,7 +213,7 @@ struct Axis {      // per-voxel invariants of projectPointToVector(pt, centre, n
     V3 a, ab;
     float ab_ab;
 };
-__device__ __forceinline__ Axis make_axis(const GridParams& g, V3 centre, V3 n) {
+PCF_HD Axis make_axis(const GridParams& g, V3 centre, V3 n) {
     V3 d = g.ball_radius_f * n;      // n * float(kBballRadius): commutative per component
     Axis ax;
     ax.a = centre - d;
@@ -119,7 +222,7 @@ __device__ __forceinline__ Axis make_axis(const GridParams& g, V3 centre, V3 n) 
     ax.ab_ab = dot(ax.ab, ax.ab);
     return ax;
 }
-__device__ __forceinline__ V3 project(const Axis& ax, V3 pt) {
+PCF_HD V3 project(const Axis& ax, V3 pt) {
     V3 ap = ax.a - pt;
     float t = dot(ap, ax.ab) / ax.ab_ab;
     return ax.a - t * ax.ab;
@@ -130,10 +233,10 @@ struct Stats {     // the scored part of VoxelInfo (OG.hpp:64-68,73); mean_dist 
     float sd_dist, mean_dist;
     int count;
 };
-__device__ __forceinline__ void stats_init(Stats& s) {
+PCF_HD void stats_init(Stats& s) {
     s.centroid = mk(0, 0, 0); s.sd = mk(0, 0, 0); s.sd_dist = 0.f; s.mean_dist = 0.f; s.count = 0;
 }
-__device__ __forceinline__ void score_point(const GridParams& g, const Axis& ax, Stats& s, V3 pt) {
+PCF_HD void score_point(const GridParams& g, const Axis& ax, Stats& s, V3 pt) {
     V3 proj = project(ax, pt);
     V3 diff = pt - proj;
     double dist = (double)sqrtf(sqnorm(diff));
@@ -155,17 +258,17 @@ __device__ __forceinline__ void score_point(const GridParams& g, const Axis& ax,
 
 // ---- PCA normal ---------------------------------------------------------------------------------------------
 struct CovAccum { float a[9]; };
-__device__ __forceinline__ void cov_init(CovAccum& c) {
+PCF_HD void cov_init(CovAccum& c) {
 #pragma unroll
     for (int i = 0; i < 9; i++) c.a[i] = 0.f;
 }
-__device__ __forceinline__ void cov_add(CovAccum& c, float x, float y, float z) {
+PCF_HD void cov_add(CovAccum& c, float x, float y, float z) {
     c.a[0] += x * x; c.a[1] += x * y; c.a[2] += x * z;
     c.a[3] += y * y; c.a[4] += y * z; c.a[5] += z * z;
     c.a[6] += x; c.a[7] += y; c.a[8] += z;
 }
 // -> symmetric covariance m00,m01,m02,m11,m12,m22
-__device__ __forceinline__ void cov_finish(CovAccum& c, int n, float m[6]) {
+PCF_HD void cov_finish(CovAccum& c, int n, float m[6]) {
     float fn = (float)n;
 #pragma unroll
     for (int i = 0; i < 9; i++) c.a[i] = c.a[i] / fn;
@@ -177,10 +280,10 @@ __device__ __forceinline__ void cov_finish(CovAccum& c, int n, float m[6]) {
     m[5] = c.a[5] - c.a[8] * c.a[8];
 }
 
-__device__ __forceinline__ float roots2_smallest() { return 0.0f; }   // computeRoots2 sets roots(0) = 0
+PCF_HD float roots2_smallest() { return 0.0f; }   // computeRoots2 sets roots(0) = 0
 
 // smallest root of the characteristic polynomial of the scaled matrix (pcl::computeRoots)
-__device__ __forceinline__ float smallest_root(float m00, float m01, float m02, float m11, float m12, float m22) {
+PCF_HD float smallest_root(float m00, float m01, float m02, float m11, float m12, float m22) {
     float c0 = m00 * m11 * m22 + 2.0f * m01 * m02 * m12 - m00 * m12 * m12 - m11 * m02 * m02 - m22 * m01 * m01;
     float c1 = m00 * m11 - m01 * m01 + m00 * m22 - m02 * m02 + m11 * m22 - m12 * m12;
     float c2 = m00 + m11 + m22;
@@ -212,7 +315,7 @@ __device__ __forceinline__ float smallest_root(float m00, float m01, float m02, 
 }
 
 // pcl::eigen33(mat, eigenvalue, eigenvector): eigenvector of the smallest eigenvalue
-__device__ __forceinline__ V3 eigen33_smallest(const float m[6]) {
+PCF_HD V3 eigen33_smallest(const float m[6]) {
     float scale = fmaxf(fmaxf(fmaxf(fabsf(m[0]), fabsf(m[1])), fmaxf(fabsf(m[2]), fabsf(m[3]))),
                         fmaxf(fabsf(m[4]), fabsf(m[5])));
     if (scale <= FLT_MIN) scale = 1.0f;

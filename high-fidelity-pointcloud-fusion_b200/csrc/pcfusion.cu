@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -34,6 +35,9 @@ struct pcf_ctx {
     pcf_config cfg{};
     GridParams g{};
     int device = 0;
+    int sm_count = 148;
+    int ctas_per_sm = kBulkMinBlocks;     // persistent CTAs per SM of the bulk kernel
+    bool use_bulk = true;                 // PCF_INGEST=generic forces the plain-load kernel (A/B measurements)
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     std::string err;
     bool started = false;
@@ -108,6 +112,12 @@ int fail(pcf_ctx* c, int code, const char* fmt, ...) {
     do {                                                         \
         kernel<<<(grid), (block), 0, (c)->stream>>>(__VA_ARGS__); \
         (c)->stats.kernel_launches++;                            \
+    } while (0)
+
+#define LAUNCH_SMEM(c, kernel, grid, block, smem, ...)              \
+    do {                                                             \
+        kernel<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__); \
+        (c)->stats.kernel_launches++;                                \
     } while (0)
 
 inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
@@ -270,8 +280,10 @@ int flush_holders(pcf_ctx* c) {
 
 // one launch over `nf` equally sized clouds resident in device memory
 int launch_ingest(pcf_ctx* c, const float* pts_dev, uint64_t frame_stride, uint32_t n, uint32_t nf, uint32_t stride,
-                  const double* poses, uint32_t first_frame_idx) {
-    static thread_local IngestBatch b;     // 12 KB of kernel parameters
+                  const double* poses, uint32_t first_frame_idx, const float* explicit_vp = nullptr,
+                  const GridParams* gp = nullptr) {
+    static thread_local IngestBatch b;     // 24 KB of kernel parameters (limit: 32 KB)
+    const GridParams& g = gp ? *gp : c->g;
     uint32_t chunks = div_up(n, kWChunk);
     b.pts = pts_dev;
     b.frame_stride = frame_stride;
@@ -280,13 +292,25 @@ int launch_ingest(pcf_ctx* c, const float* pts_dev, uint64_t frame_stride, uint3
     b.first_frame_idx = first_frame_idx;
     b.chunk_base = c->n_chunks;
     b.chunks_per_frame = chunks;
-    b.pad = 0;
+    b.explicit_vp = explicit_vp ? 1u : 0u;
+    for (int i = 0; i < 3; i++) b.vp[i] = explicit_vp ? explicit_vp[i] : 0.f;
+    b.vp[3] = 1.f;
     for (uint32_t f = 0; f < nf; f++)
         for (int i = 0; i < 12; i++) b.T[f][i] = poses[(size_t)f * 16 + i];
-    dim3 grid(div_up(chunks, kWarps), nf, 1);
-    if (stride == 4) LAUNCH(c, k_ingest<4>, grid, kBlock, b, stride, c->g, c->first_frame, c->log, c->chunk_count, c->vp_table);
-    else if (stride == 3) LAUNCH(c, k_ingest<3>, grid, kBlock, b, stride, c->g, c->first_frame, c->log, c->chunk_count, c->vp_table);
-    else LAUNCH(c, k_ingest<0>, grid, kBlock, b, stride, c->g, c->first_frame, c->log, c->chunk_count, c->vp_table);
+    // B200 path: bulk-async ring (needs 16-byte aligned chunks); anything else takes the generic kernel
+    const bool aligned = ((uintptr_t)pts_dev % 16 == 0) && ((frame_stride * 4) % 16 == 0 || nf == 1);
+    const uint32_t total = chunks * nf;
+    const uint32_t grid_bulk = std::min<uint32_t>((uint32_t)(c->sm_count * c->ctas_per_sm), div_up(total, kWarps));
+    if (c->use_bulk && aligned && stride == 4) {
+        LAUNCH_SMEM(c, (k_ingest_bulk<16, kBulkMinBlocks, kBulkRounds>), grid_bulk, kBlock, kWarps * kWChunk * 16, b, g, c->first_frame, c->log, c->chunk_count, c->vp_table);
+    } else if (c->use_bulk && aligned && stride == 3 && n % 4 == 0) {
+        LAUNCH_SMEM(c, (k_ingest_bulk<12, kBulkMinBlocks, kBulkRounds>), grid_bulk, kBlock, kWarps * kWChunk * 12, b, g, c->first_frame, c->log, c->chunk_count, c->vp_table);
+    } else {
+        dim3 grid(div_up(chunks, kWarps), nf, 1);
+        if (stride == 4) LAUNCH(c, k_ingest<4>, grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->vp_table);
+        else if (stride == 3) LAUNCH(c, k_ingest<3>, grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->vp_table);
+        else LAUNCH(c, k_ingest<0>, grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->vp_table);
+    }
     CU(cudaGetLastError());
     c->n_chunks += chunks * nf;
     return PCF_OK;
@@ -543,6 +567,13 @@ int pcf_create(const pcf_config* cfg, pcf_ctx** out) {
     auto bail = [&](int code) { g_create_error = ctx->err; destroy_impl(ctx); return code; };
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, PCF_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(PCF_ERR_CUDA); } } while (0)
     CUC(cudaSetDevice(c->device));
+    CUC(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
+    CUC(cudaFuncSetAttribute(k_ingest_bulk<16, kBulkMinBlocks, kBulkRounds>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * kWChunk * 16));
+    CUC(cudaFuncSetAttribute(k_ingest_bulk<12, kBulkMinBlocks, kBulkRounds>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * kWChunk * 12));
+    {
+        const char* e = getenv("PCF_INGEST");
+        c->use_bulk = !(e && strcmp(e, "generic") == 0);
+    }
     CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     c->n_words = (c->g.cells + 31) / 32;
