@@ -46,7 +46,7 @@ class _Stats(C.Structure):
 
 ABI_SYMBOLS = [
     "pcf_default_config", "pcf_create", "pcf_destroy", "pcf_last_error", "pcf_dims", "pcf_start", "pcf_stop", "pcf_reset",
-    "pcf_push_frame", "pcf_push_frames_device", "pcf_sync", "pcf_count_kept", "pcf_update", "pcf_extract", "pcf_process", "pcf_write_result",
+    "pcf_push_frame", "pcf_add_points", "pcf_host_alloc", "pcf_host_free", "pcf_upload_ticket", "pcf_wait_upload", "pcf_push_frames_device", "pcf_sync", "pcf_count_kept", "pcf_update", "pcf_extract", "pcf_process", "pcf_write_result",
     "pcf_extract_hq", "pcf_clear", "pcf_dump_state", "pcf_get_stats", "pcf_reset_stats", "pcf_last_timings", "pcf_stream",
     "pcf_grid_buffer", "pcf_viewpoint_table", "pcf_log_compact", "pcf_log_replace", "pcf_set_slab", "pcf_plane_counts", "pcf_kat_transform_voxel",
     "pcf_kat_normal", "pcf_kat_score",
@@ -76,6 +76,13 @@ def load_library():
     for name in ["pcf_start", "pcf_stop", "pcf_reset", "pcf_sync", "pcf_update", "pcf_clear", "pcf_reset_stats"]:
         getattr(lib, name).argtypes = [vp]
     lib.pcf_push_frame.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32]
+    lib.pcf_add_points.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32]
+    lib.pcf_host_alloc.argtypes = [C.c_size_t]
+    lib.pcf_host_alloc.restype = vp
+    lib.pcf_host_free.argtypes = [vp]
+    lib.pcf_host_free.restype = None
+    lib.pcf_upload_ticket.argtypes = [vp, C.POINTER(C.c_uint64)]
+    lib.pcf_wait_upload.argtypes = [vp, C.c_uint64]
     lib.pcf_push_frames_device.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_uint32]
     lib.pcf_count_kept.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.pcf_extract.argtypes = [vp, C.POINTER(_Result)]
@@ -204,6 +211,12 @@ class Fusion:
         pose = np.ascontiguousarray(pose, np.float64).reshape(16)
         n, stride = pts.shape
         return self._ck(self.lib.pcf_push_frame(self.h, _ptr(pts), n, stride, pose.ctypes.data, frame_idx))
+
+    def add_points(self, pts_world, viewpoint, frame_idx):
+        """OccupancyGrid::addPoints (OG.hpp:185): cloud already in the fusion frame + explicit viewpoint."""
+        vp3 = np.ascontiguousarray(viewpoint, np.float32).reshape(3)
+        n, stride = pts_world.shape
+        return self._ck(self.lib.pcf_add_points(self.h, _ptr(pts_world), n, stride, vp3.ctypes.data, frame_idx))
 
     def push_frames_device(self, pts_dev, n_frames, n_per_frame, stride, poses, first_frame_idx):
         poses = np.ascontiguousarray(poses, np.float64).reshape(n_frames, 16)

@@ -27,6 +27,7 @@ struct DevBuf {   // grow-only device allocation
 };
 
 constexpr int kRing = 4;           // staging slots for host frames
+constexpr int kTickets = 16;       // upload-completion events kept (newer uploads imply older ones)
 constexpr uint32_t kMaxChunks = 1u << 24;   // slot index must fit 32 bits: 2^24 chunks * 256
 
 }  // namespace
@@ -70,6 +71,8 @@ struct pcf_ctx {
     size_t stage_cap[kRing] = {};
     cudaEvent_t ev_copied[kRing] = {}, ev_free[kRing] = {};
     int ring_pos = 0;
+    cudaEvent_t ev_upload[kTickets] = {};
+    uint64_t uploads = 0;                 // ticket of the most recent host push
 
     // scratch
     DevBuf scan1, scan2, tmpA, tmpB, tmpC, tmpD, hist, keysA, keysB, valsA, valsB, sorted, uv_cell, uv_off, nidx,
@@ -280,10 +283,9 @@ int flush_holders(pcf_ctx* c) {
 
 // one launch over `nf` equally sized clouds resident in device memory
 int launch_ingest(pcf_ctx* c, const float* pts_dev, uint64_t frame_stride, uint32_t n, uint32_t nf, uint32_t stride,
-                  const double* poses, uint32_t first_frame_idx, const float* explicit_vp = nullptr,
-                  const GridParams* gp = nullptr) {
+                  const double* poses, uint32_t first_frame_idx, const float* explicit_vp = nullptr) {
     static thread_local IngestBatch b;     // 24 KB of kernel parameters (limit: 32 KB)
-    const GridParams& g = gp ? *gp : c->g;
+    const GridParams& g = c->g;
     uint32_t chunks = div_up(n, kWChunk);
     b.pts = pts_dev;
     b.frame_stride = frame_stride;
@@ -298,6 +300,13 @@ int launch_ingest(pcf_ctx* c, const float* pts_dev, uint64_t frame_stride, uint3
     for (uint32_t f = 0; f < nf; f++)
         for (int i = 0; i < 12; i++) b.T[f][i] = poses[(size_t)f * 16 + i];
     // B200 path: bulk-async ring (needs 16-byte aligned chunks); anything else takes the generic kernel
+    if (explicit_vp) {       // pcf_add_points: cloud already in the fusion frame
+        dim3 grid(div_up(chunks, kWarps), nf, 1);
+        LAUNCH(c, (k_ingest<0, true>), grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->vp_table);
+        CU(cudaGetLastError());
+        c->n_chunks += chunks * nf;
+        return PCF_OK;
+    }
     const bool aligned = ((uintptr_t)pts_dev % 16 == 0) && ((frame_stride * 4) % 16 == 0 || nf == 1);
     const uint32_t total = chunks * nf;
     const uint32_t grid_bulk = std::min<uint32_t>((uint32_t)(c->sm_count * c->ctas_per_sm), div_up(total, kWarps));
@@ -494,6 +503,7 @@ void destroy_impl(pcf_ctx* c) {
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
     }
+    for (int i = 0; i < kTickets; i++) if (c->ev_upload[i]) cudaEventDestroy(c->ev_upload[i]);
     if (c->total_host) cudaFreeHost(c->total_host);
     if (c->res_host) cudaFreeHost(c->res_host);
     if (c->st_host) cudaFreeHost(c->st_host);
@@ -583,6 +593,7 @@ int pcf_create(const pcf_config* cfg, pcf_ctx** out) {
     CUC(cudaMalloc(&c->occ_rank, (c->n_words + 2) * 4));
     CUC(cudaMalloc(&c->vp_table, (size_t)c->cfg.max_frames * sizeof(float4)));
     CUC(cudaMallocHost(&c->total_host, 64));
+    for (int i = 0; i < kTickets; i++) CUC(cudaEventCreateWithFlags(&c->ev_upload[i], cudaEventDisableTiming));
     for (int i = 0; i < kRing; i++) {
         CUC(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
@@ -620,7 +631,8 @@ int pcf_reset(pcf_ctx* c) {
     return PCF_OK;
 }
 
-int pcf_push_frame(pcf_ctx* c, const float* pts_host, uint32_t n, uint32_t stride, const double pose[16], uint32_t frame_idx) {
+static int push_host_cloud(pcf_ctx* c, const float* pts_host, uint32_t n, uint32_t stride, const double pose[16],
+                           const float* explicit_vp, uint32_t frame_idx) {
     if (!c) return PCF_ERR_INVALID;
     if (!c->started) return PCF_DROPPED;
     if ((!pts_host && n) || !pose || stride < 3) return fail(c, PCF_ERR_INVALID, "bad frame arguments");
@@ -645,9 +657,11 @@ int pcf_push_frame(pcf_ctx* c, const float* pts_host, uint32_t n, uint32_t strid
     CU(cudaStreamWaitEvent(c->copy_stream, c->ev_free[s], 0));
     if (bytes) CU(cudaMemcpyAsync(c->stage[s], pts_host, bytes, cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaEventRecord(c->ev_copied[s], c->copy_stream));
+    c->uploads++;
+    CU(cudaEventRecord(c->ev_upload[c->uploads % kTickets], c->copy_stream));
     CU(cudaStreamWaitEvent(c->stream, c->ev_copied[s], 0));
     if (chunks) {
-        rc = launch_ingest(c, c->stage[s], 0, n, 1, stride, pose, frame_idx);
+        rc = launch_ingest(c, c->stage[s], 0, n, 1, stride, pose, frame_idx, explicit_vp);
         if (rc) return rc;
     }
     CU(cudaEventRecord(c->ev_free[s], c->stream));
@@ -659,6 +673,37 @@ int pcf_push_frame(pcf_ctx* c, const float* pts_host, uint32_t n, uint32_t strid
     c->stats.h2d_bytes += bytes;
     return PCF_OK;
 }
+
+int pcf_push_frame(pcf_ctx* c, const float* pts_host, uint32_t n, uint32_t stride, const double pose[16], uint32_t frame_idx) {
+    return push_host_cloud(c, pts_host, n, stride, pose, nullptr, frame_idx);
+}
+
+int pcf_add_points(pcf_ctx* c, const float* pts_host, uint32_t n, uint32_t stride, const float viewpoint[3], uint32_t frame_idx) {
+    static const double identity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    if (!viewpoint) return c ? fail(c, PCF_ERR_INVALID, "null viewpoint") : PCF_ERR_INVALID;
+    return push_host_cloud(c, pts_host, n, stride, identity, viewpoint, frame_idx);
+}
+
+int pcf_upload_ticket(pcf_ctx* c, uint64_t* ticket) {
+    if (!c || !ticket) return PCF_ERR_INVALID;
+    *ticket = c->uploads;
+    return PCF_OK;
+}
+int pcf_wait_upload(pcf_ctx* c, uint64_t ticket) {
+    if (!c) return PCF_ERR_INVALID;
+    if (ticket == 0 || ticket > c->uploads) return PCF_OK;
+    // copies complete in order on the copy stream: if the ticket's event has been recycled by a newer upload,
+    // waiting for that newer one is a (stronger) valid wait
+    CU(cudaEventSynchronize(c->ev_upload[ticket % kTickets]));
+    return PCF_OK;
+}
+
+void* pcf_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void pcf_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int pcf_push_frames_device(pcf_ctx* c, const float* pts_dev, uint32_t n_frames, uint32_t n_per_frame, uint32_t stride,
                            const double* poses, uint32_t first_frame_idx) {

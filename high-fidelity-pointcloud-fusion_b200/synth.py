@@ -173,3 +173,20 @@ def wavy_sheets_world(n_sheets=4, n_side=200, res=0.001, box_half=0.5, pts_per_v
         pts = (np.stack([xr, yr, zr], axis=1) + jit * np.array([1, 1, 0.3])).astype(np.float32)
         out.append((pts, np.array([0.0, 0.0, box_half * 2], dtype=np.float32)))
     return g, out
+
+
+def write_sequence(scene: Scene, path, n_frames=None, stride=4):
+    """Record `scene` as a PCFSEQ1 file (host/sequence.hpp) for the C++ replay driver: the offline stand-in for a bag
+    of `input_point_cloud` messages + tf poses (node.cpp:327-349)."""
+    import struct
+    n = scene.n_frames if n_frames is None else n_frames
+    g = scene.grid
+    res = np.float32(g.res)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<8sIIII6d3ff2d", b"PCFSEQ1\0", n, scene.points_per_frame, stride, 0, *[float(b) for b in g.box],
+                            res, res, res, 0.0, g.clip_zmin, g.clip_zmax))
+        for i in range(n):
+            pts, T = scene.frame(i)
+            f.write(np.ascontiguousarray(T, np.float64).tobytes())
+            f.write(np.ascontiguousarray(pts[:, :stride], np.float32).tobytes())
+    return path

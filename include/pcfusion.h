@@ -13,6 +13,7 @@
  */
 #ifndef PCFUSION_H
 #define PCFUSION_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -109,6 +110,21 @@ int pcf_reset(pcf_ctx* ctx);    /* node.cpp:351-359: drops not-yet-integrated in
  * frame_idx must increase from call to call on one context.  Returns PCF_DROPPED while stopped. */
 int pcf_push_frame(pcf_ctx* ctx, const float* pts_host, uint32_t n, uint32_t stride_floats,
                    const double pose[16], uint32_t frame_idx);
+/* OccupancyGrid::addPoints<N>(cloud, viewpoint), OG.hpp:185-280, verbatim: the cloud is ALREADY in the fusion frame
+ * (the caller did node.cpp:248-255,288-290 itself), no depth clip, no transform; `viewpoint` is the Eigen::Vector3f
+ * argument.  This is the entry point the C++ drop-in class (include/pcfusion/OccupancyGrid.hpp) binds; pcf_push_frame
+ * is the faster route that also moves the clip and the transform onto the GPU. */
+int pcf_add_points(pcf_ctx* ctx, const float* pts_host, uint32_t n, uint32_t stride_floats, const float viewpoint[3],
+                   uint32_t frame_idx);
+/* Pinned (page-locked) host memory for staging clouds: what the reference's deques hold (node.cpp:130-143) lives
+ * here so that pcf_push_frame's H2D copy runs at full PCIe speed and asynchronously. */
+void* pcf_host_alloc(size_t bytes);
+void pcf_host_free(void* p);
+/* Upload tickets: pcf_push_frame / pcf_add_points return before the H2D copy of a pinned cloud has finished.
+ * pcf_upload_ticket gives the ticket of the most recent push; pcf_wait_upload blocks until that push's copy (and
+ * every earlier one) is done, i.e. until the staging buffer may be refilled. */
+int pcf_upload_ticket(pcf_ctx* ctx, uint64_t* ticket);
+int pcf_wait_upload(pcf_ctx* ctx, uint64_t ticket);
 /* Same for clouds already resident in device memory: n_frames clouds of n_per_frame points each, back to
  * back, integrated by ONE launch.  poses: n_frames x 16 doubles (host).  Frames get indices
  * first_frame_idx .. first_frame_idx+n_frames-1. */

@@ -1,0 +1,108 @@
+"""The C++ host side above the C ABI: the OccupancyGrid drop-in header and the PointcloudFusion replay driver.
+
+not-gpu part: everything builds, and without a CUDA device both programs fail loudly (no CPU fallback).
+gpu part:     (a) ONE node-shaped driver source (tests/cpp/dropin_driver.cpp) compiled against the reference's own
+                  OccupancyGrid.hpp (oracle/_ref/dropin_ref, prebuilt where /root/reference is mounted) and against
+                  include/pcfusion/OccupancyGrid.hpp writes byte-identical test_cloud.pcd / meta.csv;
+              (b) host/pcf_replay (pinned staging + worker thread + start/stop/reset/process) writes the same files as the
+                  oracle fed the same frames."""
+import importlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "host")
+DROPIN = os.path.join(ROOT, "tests", "_build", "dropin_b200")
+DROPIN_REF = os.path.join(ROOT, "oracle", "_ref", "dropin_ref")
+REPLAY = os.path.join(HOST, "pcf_replay")
+
+
+@pytest.fixture(scope="module")
+def built():
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "high-fidelity-pointcloud-fusion_b200"), "all"], check=True)
+    subprocess.run(["make", "-s", "-C", HOST, "all"], check=True)
+    return True
+
+
+@pytest.fixture(scope="module")
+def sequence(tmp_path_factory):
+    synth = importlib.import_module("high-fidelity-pointcloud-fusion_b200.synth")
+    scene = synth.small_sphere(6)
+    path = str(tmp_path_factory.mktemp("seq") / "small.pcfseq")
+    synth.write_sequence(scene, path)
+    return scene, path
+
+
+def _oracle_files(oracle, scene, outdir, update_every=0, frames=None):
+    g = scene.grid
+    og = oracle.OracleGrid(g.box, g.res)
+    idx = list(range(scene.n_frames)) if frames is None else frames
+    for k, i in enumerate(idx):
+        og.add_frame(*scene.frame(i))
+        if update_every and (k + 1) % update_every == 0:
+            og.update()
+    og.update()
+    og.download()
+    og.write_files(os.path.join(outdir, "test_cloud.pcd"), os.path.join(outdir, "meta.csv"))
+
+
+def _same_files(a, b):
+    for name in ("test_cloud.pcd", "meta.csv"):
+        x, y = open(os.path.join(a, name), "rb").read(), open(os.path.join(b, name), "rb").read()
+        assert len(x) > 1000, name
+        assert x == y, f"{name} differs ({len(x)} vs {len(y)} bytes)"
+
+
+def test_host_builds_and_fails_loudly_without_gpu(built, sequence, tmp_path):
+    import torch
+    assert os.path.exists(REPLAY) and os.path.exists(DROPIN)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the no-device path cannot be exercised")
+    r = subprocess.run([REPLAY, sequence[1], "--out", str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CUDA device" in r.stderr
+    r = subprocess.run([DROPIN, sequence[1], str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CUDA device" in r.stderr
+    assert not os.path.exists(tmp_path / "test_cloud.pcd")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("update_every", [0, 2])
+def test_dropin_header_same_files_as_reference_header(built, sequence, oracle, tmp_path, update_every):
+    scene, seq = sequence
+    ours, ref = tmp_path / "ours", tmp_path / "ref"
+    ours.mkdir(); ref.mkdir()
+    subprocess.run([DROPIN, seq, str(ours), str(update_every)], check=True, capture_output=True)
+    if os.path.exists(DROPIN_REF):      # the reference's own OccupancyGrid.hpp behind the very same driver source
+        subprocess.run([DROPIN_REF, seq, str(ref), str(update_every)], check=True, capture_output=True)
+    else:                               # no prebuilt reference binary on this box: the restatement stands in
+        _oracle_files(oracle, scene, str(ref), update_every)
+    _same_files(str(ours), str(ref))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("update_every", [0, 3])
+def test_replay_driver_matches_oracle(built, sequence, oracle, tmp_path, update_every):
+    scene, seq = sequence
+    ours, ref = tmp_path / "ours", tmp_path / "ref"
+    ours.mkdir(); ref.mkdir()
+    r = subprocess.run([REPLAY, seq, "--out", str(ours), "--update-every", str(update_every), "--slots", "3"],
+                       check=True, capture_output=True, text=True)
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["ok"] and line["integrated"] == scene.n_frames and line["dropped"] == 0 and line["kernel_launches"] > 0
+    _oracle_files(oracle, scene, str(ref), update_every)
+    _same_files(str(ours), str(ref))
+
+
+@pytest.mark.gpu
+def test_replay_reset_discards_only_queued_frames(built, sequence, tmp_path):
+    """reset (node.cpp:351-359) empties the input deque and leaves the grid alone: with everything already handed to the
+    GPU nothing is lost; the accounting must add up either way."""
+    scene, seq = sequence
+    r = subprocess.run([REPLAY, seq, "--out", str(tmp_path), "--reset-after", "2", "--slots", "2"], check=True, capture_output=True, text=True)
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["ok"] and line["integrated"] + line["discarded_by_reset"] == scene.n_frames
+    assert os.path.getsize(tmp_path / "test_cloud.pcd") > 1000
