@@ -46,9 +46,10 @@ class _Stats(C.Structure):
 
 ABI_SYMBOLS = [
     "pcf_default_config", "pcf_create", "pcf_destroy", "pcf_last_error", "pcf_dims", "pcf_start", "pcf_stop", "pcf_reset",
-    "pcf_push_frame", "pcf_add_points", "pcf_host_alloc", "pcf_host_free", "pcf_upload_ticket", "pcf_wait_upload", "pcf_push_frames_device", "pcf_sync", "pcf_count_kept", "pcf_update", "pcf_extract", "pcf_process", "pcf_write_result",
+    "pcf_push_frame", "pcf_push_pointcloud2", "pcf_add_points", "pcf_host_alloc", "pcf_host_free", "pcf_upload_ticket", "pcf_wait_upload", "pcf_push_frames_device", "pcf_sync", "pcf_count_kept", "pcf_update", "pcf_extract", "pcf_process", "pcf_write_result",
     "pcf_extract_hq", "pcf_clear", "pcf_dump_state", "pcf_get_stats", "pcf_reset_stats", "pcf_last_timings", "pcf_stream",
-    "pcf_grid_buffer", "pcf_viewpoint_table", "pcf_log_compact", "pcf_log_replace", "pcf_set_slab", "pcf_plane_counts", "pcf_kat_transform_voxel",
+    "pcf_grid_buffer", "pcf_viewpoint_table", "pcf_log_compact", "pcf_log_replace", "pcf_set_slab", "pcf_plane_counts", "pcf_plane_point_counts", "pcf_exchange_counts", "pcf_exchange_scatter", "pcf_recv_buffer", "pcf_ipc_export", "pcf_ipc_open",
+    "pcf_ipc_close_all", "pcf_install_records", "pcf_kat_transform_voxel",
     "pcf_kat_normal", "pcf_kat_score",
 ]
 
@@ -76,6 +77,7 @@ def load_library():
     for name in ["pcf_start", "pcf_stop", "pcf_reset", "pcf_sync", "pcf_update", "pcf_clear", "pcf_reset_stats"]:
         getattr(lib, name).argtypes = [vp]
     lib.pcf_push_frame.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32]
+    lib.pcf_push_pointcloud2.argtypes = [vp, vp] + [C.c_uint32] * 7 + [vp, C.c_uint32]
     lib.pcf_add_points.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32]
     lib.pcf_host_alloc.argtypes = [C.c_size_t]
     lib.pcf_host_alloc.restype = vp
@@ -100,6 +102,14 @@ def load_library():
     lib.pcf_log_replace.argtypes = [vp, vp, C.c_uint64]
     lib.pcf_set_slab.argtypes = [vp, C.c_int32, C.c_int32]
     lib.pcf_plane_counts.argtypes = [vp, vp]
+    lib.pcf_plane_point_counts.argtypes = [vp, vp]
+    lib.pcf_exchange_counts.argtypes = [vp, vp, C.c_int32, vp]
+    lib.pcf_exchange_scatter.argtypes = [vp, vp, vp]
+    lib.pcf_recv_buffer.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
+    lib.pcf_ipc_export.argtypes = [vp, vp]
+    lib.pcf_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
+    lib.pcf_ipc_close_all.argtypes = [vp]
+    lib.pcf_install_records.argtypes = [vp, vp, C.c_uint64]
     lib.pcf_kat_transform_voxel.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
     lib.pcf_kat_normal.argtypes = [vp, vp, C.c_uint32, vp]
     lib.pcf_kat_score.argtypes = [vp, vp, C.c_uint32, vp, vp, vp, vp, vp, vp, vp]
@@ -212,6 +222,12 @@ class Fusion:
         n, stride = pts.shape
         return self._ck(self.lib.pcf_push_frame(self.h, _ptr(pts), n, stride, pose.ctypes.data, frame_idx))
 
+    def push_pointcloud2(self, data, width, height, point_step, row_step, offsets, pose, frame_idx):
+        """data: uint8 numpy array = sensor_msgs/PointCloud2.data; offsets = (x, y, z) field offsets in bytes."""
+        pose = np.ascontiguousarray(pose, np.float64).reshape(16)
+        return self._ck(self.lib.pcf_push_pointcloud2(self.h, _ptr(data), width, height, point_step, row_step, offsets[0], offsets[1],
+                                                      offsets[2], pose.ctypes.data, frame_idx))
+
     def add_points(self, pts_world, viewpoint, frame_idx):
         """OccupancyGrid::addPoints (OG.hpp:185): cloud already in the fusion frame + explicit viewpoint."""
         vp3 = np.ascontiguousarray(viewpoint, np.float32).reshape(3)
@@ -302,6 +318,45 @@ class Fusion:
         out = np.zeros(self.dims[0] + 2, np.uint32)
         self._ck(self.lib.pcf_plane_counts(self.h, out.ctypes.data))
         return out
+
+    # ---- exchange v2 (slab-routed records) ----
+    def plane_point_counts(self):
+        out = np.zeros(self.dims[0] + 1, np.uint32)
+        self._ck(self.lib.pcf_plane_point_counts(self.h, out.ctypes.data))
+        return out
+
+    def exchange_counts(self, bounds):
+        b = np.ascontiguousarray(bounds, np.int32)
+        out = np.zeros(len(b) - 1, np.uint64)
+        self._ck(self.lib.pcf_exchange_counts(self.h, b.ctypes.data, len(b) - 1, out.ctypes.data))
+        return out
+
+    def exchange_scatter(self, dst_ptrs, dst_offsets):
+        p = np.ascontiguousarray(dst_ptrs, np.uint64)
+        o = np.ascontiguousarray(dst_offsets, np.uint64)
+        self._ck(self.lib.pcf_exchange_scatter(self.h, p.ctypes.data, o.ctypes.data))
+
+    def recv_buffer(self, n_records) -> int:
+        p = C.c_void_p()
+        self._ck(self.lib.pcf_recv_buffer(self.h, int(n_records), C.byref(p)))
+        return p.value
+
+    def ipc_export(self) -> bytes:
+        buf = (C.c_char * 64)()
+        self._ck(self.lib.pcf_ipc_export(self.h, buf))
+        return bytes(buf)
+
+    def ipc_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        buf = (C.c_char * 64).from_buffer_copy(handle)
+        self._ck(self.lib.pcf_ipc_open(self.h, buf, C.byref(p)))
+        return p.value
+
+    def ipc_close_all(self):
+        self._ck(self.lib.pcf_ipc_close_all(self.h))
+
+    def install_records(self, records_dev, n_records):
+        self._ck(self.lib.pcf_install_records(self.h, _ptr(records_dev), int(n_records)))
 
     # ---- known-answer hooks ----
     def kat_transform_voxel(self, pts, pose):

@@ -5,6 +5,7 @@
 // There is deliberately no CPU fallback: without a CUDA device pcf_create fails with PCF_ERR_NO_DEVICE.
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -38,6 +39,7 @@ struct pcf_ctx {
     int device = 0;
     int sm_count = 148;
     int ctas_per_sm = kBulkMinBlocks;     // persistent CTAs per SM of the bulk kernel
+    bool trace = false;                   // PCF_TRACE=1
     bool use_bulk = true;                 // PCF_INGEST=generic forces the plain-load kernel (A/B measurements)
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     std::string err;
@@ -56,6 +58,7 @@ struct pcf_ctx {
     // point log
     float4* log = nullptr;
     uint32_t* chunk_count = nullptr;
+    uint32_t* chunk_frame = nullptr;      // frame_idx of every log chunk (the exchange ships it with the records)
     uint32_t cap_chunks = 0, n_chunks = 0;
     // normals (append-only records)
     DevBuf n_cell, n_nrm, n_mark;
@@ -65,6 +68,12 @@ struct pcf_ctx {
     int64_t last_frame_idx = -1;
     int32_t slab_lo = 0, slab_hi = -1;               // x-range owned by this context; hi < 0 = whole grid
     DevBuf dense_log;
+    // frame-sharded exchange
+    ExchangePlan plan{};
+    bool plan_valid = false;
+    void* recv_buf = nullptr;             // receive buffer of the exchange (plain cudaMalloc so that it can be IPC-exported)
+    size_t recv_cap = 0;
+    std::vector<void*> ipc_opened;
 
     // staging for host frames
     float* stage[kRing] = {};
@@ -111,16 +120,29 @@ int fail(pcf_ctx* c, int code, const char* fmt, ...) {
             return fail(c, PCF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// PCF_TRACE=1: synchronise after every launch and print its name and duration (debugging / per-kernel tables)
+#define TRACE_BEGIN(c) std::chrono::steady_clock::time_point t0_; if ((c)->trace) { cudaStreamSynchronize((c)->stream); t0_ = std::chrono::steady_clock::now(); }
+#define TRACE_END(c, name)                                                                                         \
+    if ((c)->trace) {                                                                                              \
+        cudaError_t e_ = cudaStreamSynchronize((c)->stream);                                                       \
+        fprintf(stderr, "[pcf] %-48s %10.3f ms %s\n", name,                                                         \
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0_).count(),          \
+                e_ == cudaSuccess ? "" : cudaGetErrorString(e_));                                                  \
+    }
 #define LAUNCH(c, kernel, grid, block, ...)                      \
     do {                                                         \
+        TRACE_BEGIN(c)                                           \
         kernel<<<(grid), (block), 0, (c)->stream>>>(__VA_ARGS__); \
         (c)->stats.kernel_launches++;                            \
+        TRACE_END(c, #kernel)                                    \
     } while (0)
 
 #define LAUNCH_SMEM(c, kernel, grid, block, smem, ...)              \
     do {                                                             \
+        TRACE_BEGIN(c)                                               \
         kernel<<<(grid), (block), (smem), (c)->stream>>>(__VA_ARGS__); \
         (c)->stats.kernel_launches++;                                \
+        TRACE_END(c, #kernel)                                        \
     } while (0)
 
 inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
@@ -229,18 +251,22 @@ int ensure_log(pcf_ctx* c, uint32_t need_chunks) {
     if (need_chunks > kMaxChunks) return fail(c, PCF_ERR_CAPACITY, "point log limit reached (%u chunks of %d input points)", kMaxChunks, kWChunk);
     uint32_t cap = std::max<uint32_t>(need_chunks, std::min<uint64_t>((uint64_t)c->cap_chunks * 2, kMaxChunks));
     float4* nl = nullptr;
-    uint32_t* nc = nullptr;
+    uint32_t *nc = nullptr, *nfr = nullptr;
     CU(cudaMalloc(&nl, (size_t)cap * kWChunk * sizeof(float4)));
     CU(cudaMalloc(&nc, (size_t)cap * 4));
+    CU(cudaMalloc(&nfr, (size_t)cap * 4));
     if (c->n_chunks) {
         CU(cudaMemcpyAsync(nl, c->log, (size_t)c->n_chunks * kWChunk * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
         CU(cudaMemcpyAsync(nc, c->chunk_count, (size_t)c->n_chunks * 4, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(nfr, c->chunk_frame, (size_t)c->n_chunks * 4, cudaMemcpyDeviceToDevice, c->stream));
     }
     CU(cudaStreamSynchronize(c->stream));
     if (c->log) CU(cudaFree(c->log));
     if (c->chunk_count) CU(cudaFree(c->chunk_count));
+    if (c->chunk_frame) CU(cudaFree(c->chunk_frame));
     c->log = nl;
     c->chunk_count = nc;
+    c->chunk_frame = nfr;
     c->cap_chunks = cap;
     return PCF_OK;
 }
@@ -302,7 +328,7 @@ int launch_ingest(pcf_ctx* c, const float* pts_dev, uint64_t frame_stride, uint3
     // B200 path: bulk-async ring (needs 16-byte aligned chunks); anything else takes the generic kernel
     if (explicit_vp) {       // pcf_add_points: cloud already in the fusion frame
         dim3 grid(div_up(chunks, kWarps), nf, 1);
-        LAUNCH(c, (k_ingest<0, true>), grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->vp_table);
+        LAUNCH(c, (k_ingest<0, true>), grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
         CU(cudaGetLastError());
         c->n_chunks += chunks * nf;
         return PCF_OK;
@@ -311,14 +337,14 @@ int launch_ingest(pcf_ctx* c, const float* pts_dev, uint64_t frame_stride, uint3
     const uint32_t total = chunks * nf;
     const uint32_t grid_bulk = std::min<uint32_t>((uint32_t)(c->sm_count * c->ctas_per_sm), div_up(total, kWarps));
     if (c->use_bulk && aligned && stride == 4) {
-        LAUNCH_SMEM(c, (k_ingest_bulk<16, kBulkMinBlocks, kBulkRounds>), grid_bulk, kBlock, kWarps * kWChunk * 16, b, g, c->first_frame, c->log, c->chunk_count, c->vp_table);
+        LAUNCH_SMEM(c, (k_ingest_bulk<16, kBulkMinBlocks, kBulkRounds>), grid_bulk, kBlock, kWarps * kWChunk * 16, b, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
     } else if (c->use_bulk && aligned && stride == 3 && n % 4 == 0) {
-        LAUNCH_SMEM(c, (k_ingest_bulk<12, kBulkMinBlocks, kBulkRounds>), grid_bulk, kBlock, kWarps * kWChunk * 12, b, g, c->first_frame, c->log, c->chunk_count, c->vp_table);
+        LAUNCH_SMEM(c, (k_ingest_bulk<12, kBulkMinBlocks, kBulkRounds>), grid_bulk, kBlock, kWarps * kWChunk * 12, b, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
     } else {
         dim3 grid(div_up(chunks, kWarps), nf, 1);
-        if (stride == 4) LAUNCH(c, k_ingest<4>, grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->vp_table);
-        else if (stride == 3) LAUNCH(c, k_ingest<3>, grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->vp_table);
-        else LAUNCH(c, k_ingest<0>, grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->vp_table);
+        if (stride == 4) LAUNCH(c, k_ingest<4>, grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
+        else if (stride == 3) LAUNCH(c, k_ingest<3>, grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
+        else LAUNCH(c, k_ingest<0>, grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
     }
     CU(cudaGetLastError());
     c->n_chunks += chunks * nf;
@@ -415,10 +441,18 @@ int run_scoring(pcf_ctx* c) {
     if ((rc = reserve(c, c->sc_c, (size_t)nn * 4))) return rc;
     LAUNCH(c, k_map_normals, div_up(nn, kBlock), kBlock, (const uint32_t*)c->n_cell.p, nn, c->occ_bits, c->occ_rank, (uint32_t*)c->nidx.p);
     ScoreOut so{(float4*)c->sc_a.p, (float4*)c->sc_b.p, (float*)c->sc_c.p};
+    uint32_t* fault = (uint32_t*)c->total_dev.p + 8;
+    CU(cudaMemsetAsync(fault, 0, 32, c->stream));
     LAUNCH(c, k_score, div_up(nn, 128), 128, (const uint32_t*)c->n_cell.p, (const float4*)c->n_nrm.p, (const uint32_t*)c->n_mark.p, nn,
            c->g, c->occ_bits, c->occ_rank, (const uint32_t*)c->uv_off.p, (const uint32_t*)c->nidx.p, (const float4*)c->sorted.p,
-           (const uint32_t*)c->holder, so);
+           (const uint32_t*)c->holder, so, (uint32_t)c->n_points, (const uint32_t*)c->uv_cell.p, fault);
     CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->total_host + 8, fault, 32, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->total_host[8]) {
+        const uint32_t* f = c->total_host + 8;
+        return fail(c, PCF_ERR_INTERNAL, "k_score consistency fault %u: voxel record %u, words %u %u %u %u %u", f[0], f[1], f[2], f[3], f[4], f[5], f[6]);
+    }
     return PCF_OK;
 }
 
@@ -496,13 +530,14 @@ void destroy_impl(pcf_ctx* c) {
                       &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->sorted, &c->uv_cell, &c->uv_off, &c->nidx, &c->sc_a, &c->sc_b,
                       &c->sc_c, &c->flags, &c->slots, &c->cand, &c->res_dev, &c->total_dev, &c->dense_log};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
-    void* raw[] = {c->first_frame, c->holder, c->nrm_bits, c->occ_bits, c->occ_rank, c->vp_table, c->log, c->chunk_count};
+    void* raw[] = {c->first_frame, c->holder, c->nrm_bits, c->occ_bits, c->occ_rank, c->vp_table, c->log, c->chunk_count, c->chunk_frame, c->recv_buf};
     for (void* p : raw) if (p) cudaFree(p);
     for (int i = 0; i < kRing; i++) {
         if (c->stage[i]) cudaFree(c->stage[i]);
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
     }
+    for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     for (int i = 0; i < kTickets; i++) if (c->ev_upload[i]) cudaEventDestroy(c->ev_upload[i]);
     if (c->total_host) cudaFreeHost(c->total_host);
     if (c->res_host) cudaFreeHost(c->res_host);
@@ -581,6 +616,8 @@ int pcf_create(const pcf_config* cfg, pcf_ctx** out) {
     CUC(cudaFuncSetAttribute(k_ingest_bulk<16, kBulkMinBlocks, kBulkRounds>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * kWChunk * 16));
     CUC(cudaFuncSetAttribute(k_ingest_bulk<12, kBulkMinBlocks, kBulkRounds>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * kWChunk * 12));
     {
+        const char* t = getenv("PCF_TRACE");
+        c->trace = t && atoi(t) > 0;
         const char* e = getenv("PCF_INGEST");
         c->use_bulk = !(e && strcmp(e, "generic") == 0);
     }
@@ -676,6 +713,29 @@ static int push_host_cloud(pcf_ctx* c, const float* pts_host, uint32_t n, uint32
 
 int pcf_push_frame(pcf_ctx* c, const float* pts_host, uint32_t n, uint32_t stride, const double pose[16], uint32_t frame_idx) {
     return push_host_cloud(c, pts_host, n, stride, pose, nullptr, frame_idx);
+}
+
+// sensor_msgs/PointCloud2 front end (node.cpp:182-216): x, y, z are consecutive float32 fields `x_offset` bytes into
+// every `point_step`-byte point.  Unlike the reference, which walks only the first `row_step` bytes (D6), every row
+// of an organized cloud is integrated.  The bytes are uploaded as they are; the kernel strides over them.
+int pcf_push_pointcloud2(pcf_ctx* c, const uint8_t* data, uint32_t width, uint32_t height, uint32_t point_step, uint32_t row_step,
+                         uint32_t x_offset, uint32_t y_offset, uint32_t z_offset, const double pose[16], uint32_t frame_idx) {
+    if (!c) return PCF_ERR_INVALID;
+    if (!data || !pose) return fail(c, PCF_ERR_INVALID, "null cloud / pose");
+    if (point_step % 4 || x_offset % 4 || y_offset != x_offset + 4 || z_offset != x_offset + 8 || point_step < x_offset + 12)
+        return fail(c, PCF_ERR_INVALID, "PointCloud2 layout not supported: x, y, z must be consecutive 4-byte aligned float32 fields");
+    if (row_step < (uint64_t)width * point_step) return fail(c, PCF_ERR_INVALID, "row_step smaller than width * point_step");
+    const uint64_t n = (uint64_t)width * height;
+    if (n > 0xFFFFFFFFull) return fail(c, PCF_ERR_INVALID, "cloud too large");
+    const float* first = reinterpret_cast<const float*>(data + x_offset);
+    if (row_step == (uint64_t)width * point_step || height <= 1)
+        return push_host_cloud(c, first, (uint32_t)n, point_step / 4, pose, nullptr, frame_idx);
+    // padded rows: squeeze the padding out on the host (rare; drivers emit dense rows)
+    std::vector<uint8_t> dense((size_t)n * point_step);
+    for (uint32_t r = 0; r < height; r++) memcpy(dense.data() + (size_t)r * width * point_step, data + (size_t)r * row_step, (size_t)width * point_step);
+    int rc = push_host_cloud(c, reinterpret_cast<const float*>(dense.data() + x_offset), (uint32_t)n, point_step / 4, pose, nullptr, frame_idx);
+    if (rc == PCF_OK) CU(cudaStreamSynchronize(c->copy_stream));     // `dense` dies with this call
+    return rc;
 }
 
 int pcf_add_points(pcf_ctx* c, const float* pts_host, uint32_t n, uint32_t stride, const float viewpoint[3], uint32_t frame_idx) {
@@ -1009,6 +1069,148 @@ int pcf_plane_counts(pcf_ctx* c, uint32_t* counts_host) {
            (uint32_t*)c->tmpA.p);
     CU(cudaMemcpyAsync(counts_host, c->tmpA.p, ((size_t)np + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return PCF_OK;
+}
+
+// ---- exchange v2: slab-routed records, compaction fused with the (peer) write ---------------------------------
+int pcf_plane_point_counts(pcf_ctx* c, uint32_t* counts_host) {
+    if (!c || !counts_host) return PCF_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    uint32_t np = c->g.n1[0];
+    int rc = reserve(c, c->tmpA, (size_t)np * 4);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(c->tmpA.p, 0, (size_t)np * 4, c->stream));
+    if (c->n_chunks) {
+        uint32_t grid = std::min<uint32_t>(div_up(c->n_chunks, kWarps), (uint32_t)c->sm_count * 4);
+        k_plane_point_counts<<<grid, kBlock, (size_t)np * 4, c->stream>>>(c->log, c->chunk_count, c->n_chunks, c->g.n1[1] * c->g.n1[2], np, (uint32_t*)c->tmpA.p);
+        c->stats.kernel_launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(counts_host, c->tmpA.p, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return PCF_OK;
+}
+
+int pcf_exchange_counts(pcf_ctx* c, const int32_t* bounds, int32_t n_ranks, uint64_t* counts_host) {
+    if (!c || !bounds || !counts_host || n_ranks < 1 || n_ranks > kMaxRanks) return c ? fail(c, PCF_ERR_INVALID, "bad exchange arguments (1..%d ranks)", kMaxRanks) : PCF_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    if (c->n_normals) return fail(c, PCF_ERR_INVALID, "exchange after pcf_update: sharded merge of interleaved schedules is not supported");
+    const int32_t halo = std::max(c->g.walk_k, 2);      // +-K walk (OG.hpp:403-405) and the 5x5x5 scan (OG.hpp:334)
+    ExchangePlan& p = c->plan;
+    p.n_ranks = (uint32_t)n_ranks;
+    p.plane_cells = c->g.n1[1] * c->g.n1[2];
+    for (int d = 0; d < n_ranks; d++) {
+        if (bounds[d] < 0 || bounds[d] > bounds[d + 1] || (uint32_t)bounds[d + 1] > c->g.n1[0]) return fail(c, PCF_ERR_INVALID, "bad slab bounds");
+        bool empty = bounds[d] == bounds[d + 1];
+        p.lo[d] = empty ? 0u : (uint32_t)std::max<int32_t>(bounds[d] - halo, 0);
+        p.hi[d] = empty ? 0u : (uint32_t)std::min<int64_t>((int64_t)bounds[d + 1] + halo, c->g.n1[0]);
+        p.dst[d] = nullptr;
+    }
+    for (int d = 0; d < n_ranks; d++) counts_host[d] = 0;
+    c->plan_valid = true;
+    if (!c->n_chunks) return PCF_OK;
+    size_t n = (size_t)n_ranks * c->n_chunks;
+    int rc;
+    if ((rc = reserve(c, c->tmpC, (n + 1) * 4))) return rc;
+    if ((rc = reserve(c, c->tmpD, (n + 1) * 4))) return rc;
+    uint32_t* cnt = (uint32_t*)c->tmpC.p;
+    uint32_t* off = (uint32_t*)c->tmpD.p;
+    LAUNCH(c, k_exchange_count, div_up(c->n_chunks, kWarps), kBlock, c->log, c->chunk_count, c->n_chunks, p, cnt);
+    CU(cudaMemsetAsync(cnt + n, 0, 4, c->stream));
+    if ((rc = scan_u32(c, cnt, off, n + 1, nullptr))) return rc;       // off[n] = grand total
+    // per-destination totals = off[(d+1) * n_chunks] - off[d * n_chunks]
+    std::vector<uint32_t> edge((size_t)n_ranks + 1);
+    for (int d = 0; d <= n_ranks; d++)
+        CU(cudaMemcpyAsync(&edge[d], off + (size_t)d * c->n_chunks, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int d = 0; d < n_ranks; d++) counts_host[d] = edge[d + 1] - edge[d];
+    c->stats.d2h_bytes += 4 * (n_ranks + 1);
+    return PCF_OK;
+}
+
+int pcf_exchange_scatter(pcf_ctx* c, void* const* dst_bufs, const uint64_t* dst_offsets) {
+    if (!c || !dst_bufs || !dst_offsets) return PCF_ERR_INVALID;
+    if (!c->plan_valid) return fail(c, PCF_ERR_INVALID, "pcf_exchange_scatter without pcf_exchange_counts");
+    CU(cudaSetDevice(c->device));
+    for (uint32_t d = 0; d < c->plan.n_ranks; d++) c->plan.dst[d] = (float4*)dst_bufs[d] + dst_offsets[d];
+    if (c->n_chunks) {
+        LAUNCH(c, k_exchange_scatter, div_up(c->n_chunks, kWarps), kBlock, c->log, c->chunk_count, c->chunk_frame, c->n_chunks, c->plan,
+               (const uint32_t*)c->tmpD.p);
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(c->stream));      // the caller's barrier across ranks comes next
+    c->plan_valid = false;
+    return PCF_OK;
+}
+
+int pcf_recv_buffer(pcf_ctx* c, uint64_t n_records, void** dev_ptr) {
+    if (!c || !dev_ptr) return PCF_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    size_t bytes = std::max<size_t>((size_t)n_records, 1) * sizeof(float4);
+    if (bytes > c->recv_cap) {
+        CU(cudaStreamSynchronize(c->stream));
+        if (c->recv_buf) CU(cudaFree(c->recv_buf));
+        c->recv_buf = nullptr; c->recv_cap = 0;
+        size_t want = bytes + bytes / 8;
+        CU(cudaMalloc(&c->recv_buf, want));
+        c->recv_cap = want;
+    }
+    *dev_ptr = c->recv_buf;
+    return PCF_OK;
+}
+
+int pcf_ipc_export(pcf_ctx* c, void* handle64) {
+    if (!c || !handle64 || !c->recv_buf) return c ? fail(c, PCF_ERR_INVALID, "no receive buffer to export") : PCF_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, c->recv_buf));
+    memcpy(handle64, &h, 64);
+    return PCF_OK;
+}
+int pcf_ipc_open(pcf_ctx* c, const void* handle64, void** peer_ptr) {
+    if (!c || !handle64 || !peer_ptr) return PCF_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->ipc_opened.push_back(p);
+    *peer_ptr = p;
+    return PCF_OK;
+}
+int pcf_ipc_close_all(pcf_ctx* c) {
+    if (!c) return PCF_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+    c->ipc_opened.clear();
+    return PCF_OK;
+}
+
+int pcf_install_records(pcf_ctx* c, const void* records_dev, uint64_t n) {
+    if (!c || (!records_dev && n)) return PCF_ERR_INVALID;
+    if (n >= 0xFFFFFFFFull) return fail(c, PCF_ERR_CAPACITY, "merged log too large");
+    if (c->n_normals) return fail(c, PCF_ERR_INVALID, "pcf_install_records after pcf_update: sharded merge of interleaved schedules is not supported");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    uint32_t chunks = div_up(n, kWChunk);
+    if (chunks > kMaxChunks) return fail(c, PCF_ERR_CAPACITY, "point log limit reached");
+    c->n_chunks = 0;                       // the local log is superseded by the routed records (own ones included)
+    int rc = ensure_log(c, std::max<uint32_t>(chunks, 1));
+    if (rc) return rc;
+    LAUNCH(c, k_fill_u32, 148 * 8, 512, c->first_frame, c->g.cells, kEmpty);
+    if (n) {
+        LAUNCH(c, k_install_records, div_up(n, kBlock), kBlock, (const float4*)records_dev, n, c->g, c->first_frame, c->log);
+        LAUNCH(c, k_chunk_counts_dense, div_up(chunks, kBlock), kBlock, c->chunk_count, chunks, n);
+        CU(cudaGetLastError());
+    }
+    c->n_chunks = chunks;
+    CU(cudaStreamSynchronize(c->stream));
+    c->occ_dirty = true;
+    c->sorted_valid = false;
     return PCF_OK;
 }
 

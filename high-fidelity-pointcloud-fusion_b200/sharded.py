@@ -100,6 +100,118 @@ def merge_and_extract_local(ranks):
     return _concat_results(parts)
 
 
+# ---- exchange v2: slab-routed records, compaction fused with the peer write (pcfusion.h "exchange v2") -------------
+def slab_bounds_from_points(plane_points, world):
+    """x-plane boundaries b[0..world] with ~equal numbers of log records per slab; plane_points[x] = records in plane x
+    (summed over ranks)."""
+    pp = np.asarray(plane_points, dtype=np.int64)
+    cum = np.concatenate([[0], np.cumsum(pp)])
+    return choose_slabs(cum, world)
+
+
+def route_offsets(count_matrix):
+    """count_matrix[s][d] = records rank s sends to rank d.  Returns (offset[s][d] of s's block inside d's receive
+    buffer -- source-rank order = frame order = arrival order -- , total[d])."""
+    m = np.asarray(count_matrix, dtype=np.int64)
+    off = np.zeros_like(m)
+    off[1:] = np.cumsum(m, axis=0)[:-1]
+    return off, m.sum(axis=0)
+
+
+def merge_and_extract_local_v2(ranks):
+    """In-process emulation of exchange v2: `ranks` = contexts in frame-block order (one or several GPUs of this process).
+    Every context scatters straight into the other contexts' receive buffers (plain device pointers; across processes
+    the same pointers come from pcf_ipc_open)."""
+    world = len(ranks)
+    devs = [torch.device("cuda", f.device_index) for f in ranks]
+    for f in ranks:
+        f.sync()
+    plane = sum(f.plane_point_counts().astype(np.int64) for f in ranks)
+    bounds = slab_bounds_from_points(plane, world)
+    vps = None
+    for f, d in zip(ranks, devs):
+        vp, nf = f.viewpoint_table()
+        v = _as_tensor(vp, (nf, 4), "<f4", d).to(devs[0])
+        vps = v.clone() if vps is None else vps + v
+    counts = np.stack([f.exchange_counts(bounds) for f in ranks]).astype(np.int64)
+    off, total = route_offsets(counts)
+    bufs = [f.recv_buffer(int(total[r])) for r, f in enumerate(ranks)]
+    for s, f in enumerate(ranks):
+        f.exchange_scatter(bufs, off[s])
+    parts = []
+    for r, (f, d) in enumerate(zip(ranks, devs)):
+        vp, nf = f.viewpoint_table()
+        _as_tensor(vp, (nf, 4), "<f4", d).copy_(vps.to(d))
+        f.install_records(bufs[r], int(total[r]))
+        f.set_slab(bounds[r], bounds[r + 1])
+        f.update()
+        parts.append(f.extract())
+    return _concat_results(parts)
+
+
+class PeerExchange:
+    """One process per GPU: receive buffers mapped into every peer with CUDA IPC, so that pcf_exchange_scatter's stores
+    travel over NVLink.  Handles are re-exchanged only when a receive buffer had to grow."""
+
+    def __init__(self, fus, group=None):
+        import torch.distributed as dist
+        self.fus, self.group = fus, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.ptrs, self.cap = None, -1
+
+    def buffers(self, my_total):
+        import torch.distributed as dist
+        need = torch.tensor([int(my_total) > self.cap], dtype=torch.int32, device=torch.device("cuda", self.fus.device_index))
+        dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.group)
+        if self.ptrs is None or int(need.item()):
+            self.fus.ipc_close_all()
+            self.cap = max(int(my_total) + int(my_total) // 4, 1 << 16, self.cap)   # head-room: the next process() rarely re-maps
+            mine = self.fus.recv_buffer(self.cap)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self.fus.ipc_export(), group=self.group)
+            self.ptrs = [mine if r == self.rank else self.fus.ipc_open(handles[r]) for r in range(self.world)]
+        return self.ptrs
+
+
+def merge_and_extract_v2(fus, group=None, gather_to=0, peer=None):
+    """One process per GPU, exchange v2.  Collectives: two tiny all-reduces (plane histogram, viewpoint table), one
+    all-gather of the R x R count matrix, then ONE kernel per rank that compacts and writes into the peers' buffers,
+    and a barrier.  Returns (local slab result, merged result on rank `gather_to` else None, timings dict in ms)."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device("cuda", fus.device_index)
+    peer = peer or PeerExchange(fus, group)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    fus.sync()
+    plane = torch.from_numpy(fus.plane_point_counts().astype(np.int64)).to(dev)
+    dist.all_reduce(plane, group=group)
+    bounds = slab_bounds_from_points(plane.cpu().numpy(), world)
+    vp, nf = fus.viewpoint_table()
+    dist.all_reduce(_as_tensor(vp, (nf, 4), "<f4", dev), group=group)
+    mine = torch.from_numpy(fus.exchange_counts(bounds).astype(np.int64)).to(dev)
+    rows = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(rows, mine, group=group)
+    off, total = route_offsets(torch.stack(rows).cpu().numpy())
+    ptrs = peer.buffers(int(total[rank]))
+    dist.barrier(group=group)                 # every peer has finished reading its receive buffer from the last round
+    fus.exchange_scatter(ptrs, off[rank])
+    dist.barrier(group=group)                 # every rank's stores have landed (pcf_exchange_scatter synchronises its stream)
+    ev[1].record()
+    fus.install_records(ptrs[rank], int(total[rank]))
+    fus.set_slab(bounds[rank], bounds[rank + 1])
+    fus.update()
+    local = fus.extract()
+    ev[2].record()
+    torch.cuda.synchronize(dev)
+    timings = {"exchange_ms": ev[0].elapsed_time(ev[1]), "slab_process_ms": ev[1].elapsed_time(ev[2]),
+               "records_in": int(total[rank]), "records_out": int(mine.sum().item())}
+    parts = [None] * world if rank == gather_to else None
+    dist.gather_object(local, parts, dst=gather_to, group=group)
+    full = _concat_results(parts) if rank == gather_to else None
+    return local, full, timings
+
+
 def merge_exchange(grid, vps, log, group=None):
     """The three collectives of process(): in-place MIN on the grid, SUM on the viewpoint table, and an all-gather
     of the variable-length rank logs (rank order).  Works on CPU tensors with gloo and CUDA tensors with NCCL."""

@@ -77,7 +77,35 @@ class Scene:
         return pts, T
 
 
+def frames_on_device(scene: "Scene", first, n, device="cuda"):
+    """The same camera model evaluated with torch on the GPU: [n, H*W, 4] float32 clouds that never touch the host,
+    for the large configurations (C3 / C4) where numpy generation would dominate the run.  Noise comes from torch's
+    generator (seed 1234 + frame_idx), so these clouds are NOT bit-identical to Scene.frame(); parity tests keep using
+    the numpy path."""
+    import torch
+    dirs = torch.from_numpy(scene._dirs).to(device)
+    out = torch.zeros((n, dirs.shape[0], 4), dtype=torch.float32, device=device)
+    poses = np.stack([scene.pose(first + i) for i in range(n)])
+    gen = torch.Generator(device=device)
+    for i in range(n):
+        T = torch.from_numpy(poses[i]).to(device)
+        t = scene.surface.torch(T[:3, 3], dirs @ T[:3, :3].T)
+        gen.manual_seed(1234 + first + i)
+        t = t + torch.randn(t.shape, generator=gen, device=device, dtype=torch.float64) * scene.noise_sigma
+        out[i, :, :3] = (dirs * t[:, None]).to(torch.float32)
+    if out.is_cuda:
+        torch.cuda.synchronize(out.device)     # libpcfusion runs on its own stream: the clouds must be complete before they are pushed
+    return out, poses
+
+
 def _sphere_surface(radius):
+    def hit_torch(c, d):
+        import torch
+        b = d @ c
+        disc = b * b - (c @ c - radius * radius)
+        t = -b - torch.sqrt(disc.clamp_min(0))
+        return torch.where((disc > 0) & (t > 0), t, torch.full_like(t, float("nan")))
+
     def hit(c, d):
         b = d @ c
         disc = b * b - (c @ c - radius * radius)
@@ -86,6 +114,7 @@ def _sphere_surface(radius):
         t[ok] = -b[ok] - np.sqrt(disc[ok])
         t[t <= 0] = np.nan
         return t
+    hit.torch = hit_torch
     return hit
 
 
@@ -95,6 +124,15 @@ def _plate_surface(half, amp, period):
     def f(x, y):
         return amp * np.sin(k * x) * np.cos(k * y)
 
+    def hit_torch(c, d):
+        import torch
+        t = (0.0 - c[2]) / d[:, 2]
+        for _ in range(40):
+            x, y = c[0] + t * d[:, 0], c[1] + t * d[:, 1]
+            t = (amp * torch.sin(k * x) * torch.cos(k * y) - c[2]) / d[:, 2]
+        x, y = c[0] + t * d[:, 0], c[1] + t * d[:, 1]
+        return torch.where((x.abs() <= half) & (y.abs() <= half) & (t > 0), t, torch.full_like(t, float("nan")))
+
     def hit(c, d):
         t = (0.0 - c[2]) / d[:, 2]
         for _ in range(40):
@@ -103,6 +141,7 @@ def _plate_surface(half, amp, period):
         x, y = c[0] + t * d[:, 0], c[1] + t * d[:, 1]
         t = np.where((np.abs(x) <= half) & (np.abs(y) <= half) & (t > 0), t, np.nan)
         return t
+    hit.torch = hit_torch
     return hit
 
 

@@ -29,7 +29,8 @@ typedef enum {
     PCF_ERR_CUDA = -2,        /* CUDA runtime error (text in pcf_last_error) */
     PCF_ERR_CAPACITY = -3,    /* point log / frame table limit reached */
     PCF_ERR_IO = -4,          /* cloud / metadata file could not be written */
-    PCF_ERR_NO_DEVICE = -5    /* no usable CUDA device: the library has no CPU fallback */
+    PCF_ERR_NO_DEVICE = -5,   /* no usable CUDA device: the library has no CPU fallback */
+    PCF_ERR_INTERNAL = -6     /* a device-side consistency check failed (text in pcf_last_error) */
 } pcf_status;
 
 /* Grid + stage parameters.  Replaces the compile-time constants and ctor calls of the node:
@@ -110,6 +111,12 @@ int pcf_reset(pcf_ctx* ctx);    /* node.cpp:351-359: drops not-yet-integrated in
  * frame_idx must increase from call to call on one context.  Returns PCF_DROPPED while stopped. */
 int pcf_push_frame(pcf_ctx* ctx, const float* pts_host, uint32_t n, uint32_t stride_floats,
                    const double pose[16], uint32_t frame_idx);
+/* sensor_msgs/PointCloud2 front end = pointCloud2ToPclXYZRGBOMP (node.cpp:182-216) + the rest of pcf_push_frame: `data` is
+ * msg.data, x/y/z_offset are fields[0..2].offset (consecutive float32).  All rows of an organized cloud are used (D6);
+ * rgb is ignored, as it is downstream in the reference (OG.hpp:471-477 never reads it). */
+int pcf_push_pointcloud2(pcf_ctx* ctx, const uint8_t* data, uint32_t width, uint32_t height, uint32_t point_step,
+                         uint32_t row_step, uint32_t x_offset, uint32_t y_offset, uint32_t z_offset, const double pose[16],
+                         uint32_t frame_idx);
 /* OccupancyGrid::addPoints<N>(cloud, viewpoint), OG.hpp:185-280, verbatim: the cloud is ALREADY in the fusion frame
  * (the caller did node.cpp:248-255,288-290 itself), no depth clip, no transform; `viewpoint` is the Eigen::Vector3f
  * argument.  This is the entry point the C++ drop-in class (include/pcfusion/OccupancyGrid.hpp) binds; pcf_push_frame
@@ -171,6 +178,25 @@ int pcf_set_slab(pcf_ctx* ctx, int32_t x_lo, int32_t x_hi);
 int pcf_log_replace(pcf_ctx* ctx, const void* log_dev, uint64_t n_points);
 /* counts_host[x] = occupied voxels with plane index < x, x = 0 .. xdim+1 (for balanced slab boundaries). */
 int pcf_plane_counts(pcf_ctx* ctx, uint32_t* counts_host);
+
+/* ---- exchange v2: records routed to the owner of their x-slab, no dense grid on the wire -------------------------
+ * 1. pcf_plane_point_counts on every rank, summed over ranks by the caller -> slab bounds b[0..R] balanced by points.
+ * 2. pcf_exchange_counts(bounds): how many of this rank's records go to each destination (slab +- halo planes);
+ *    the R x R count matrix (all-gathered by the caller) gives every (source, destination) offset.
+ * 3. pcf_recv_buffer on every rank (sized by its column sum); peers map it with pcf_ipc_export / pcf_ipc_open (one
+ *    process per GPU) or simply pass the pointer (several contexts in one process).
+ * 4. pcf_exchange_scatter(dst_bufs, dst_offsets): ONE kernel compacts this rank's log per destination and writes
+ *    the (x, y, z, frame_idx) records straight into the destinations' receive buffers (NVLink peer stores).
+ * 5. barrier across ranks, then pcf_install_records(own receive buffer): recompute cells, rebuild the first-frame grid,
+ *    install the log.  pcf_set_slab + pcf_update + pcf_extract follow as before. */
+int pcf_plane_point_counts(pcf_ctx* ctx, uint32_t* counts_host /* xdim+1 entries */);
+int pcf_exchange_counts(pcf_ctx* ctx, const int32_t* bounds /* n_ranks+1 */, int32_t n_ranks, uint64_t* counts_host /* n_ranks */);
+int pcf_exchange_scatter(pcf_ctx* ctx, void* const* dst_bufs /* n_ranks device pointers */, const uint64_t* dst_offsets /* records */);
+int pcf_recv_buffer(pcf_ctx* ctx, uint64_t n_records, void** dev_ptr);
+int pcf_ipc_export(pcf_ctx* ctx, void* handle64);                          /* cudaIpcMemHandle_t of the receive buffer */
+int pcf_ipc_open(pcf_ctx* ctx, const void* handle64, void** peer_ptr);
+int pcf_ipc_close_all(pcf_ctx* ctx);
+int pcf_install_records(pcf_ctx* ctx, const void* records_dev, uint64_t n_records);
 
 /* ---- known-answer hooks: run ONE device function over an array (tests bit-compare with the oracle) ---- */
 int pcf_kat_transform_voxel(pcf_ctx* ctx, const float* pts_host, uint32_t n, uint32_t stride_floats,

@@ -175,3 +175,66 @@ def test_frame_sharded_merge_is_byte_identical(pcf, small, world):
     assert_same(got, want, RESULT_FIELDS, f"sharded x{world}: ")
     for f in ranks + [one]:
         f.close()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_exchange_v2_slab_routed_records_byte_identical(pcf, small, world):
+    """Exchange v2 (pcfusion.h): records routed to the owner of their x-slab by ONE compaction+scatter kernel per rank
+    (here into the other contexts' receive buffers on the same GPU); merged extraction == 1-rank extraction."""
+    import importlib
+    sh = importlib.import_module(pcf.__name__ + ".sharded")
+    g = small.grid
+    frames = [small.frame(i) for i in range(small.n_frames)]
+    one = pcf.Fusion(g.box, g.res)
+    for i, (pts, T) in enumerate(frames):
+        one.push_frame(pts, T, i)
+    one.update()
+    want = one.extract()
+    ranks = [pcf.Fusion(g.box, g.res) for _ in range(world)]
+    for r, f in enumerate(ranks):
+        lo, hi = sh.frame_block(len(frames), r, world)    # world 8 > 6 frames: some ranks own no frame at all
+        for i in range(lo, hi):
+            f.push_frame(frames[i][0], frames[i][1], i)
+    got = sh.merge_and_extract_local_v2(ranks)
+    assert_same(got, want, RESULT_FIELDS, f"exchange v2 x{world}: ")
+    for f in ranks + [one]:
+        f.close()
+
+
+def test_pointcloud2_front_end_and_add_points(pcf, oracle, small):
+    """a1 (node.cpp:182-216): a RealSense-style PointCloud2 (x y z at bytes 0/4/8, rgb at 16, point_step 20, padded
+    rows) gives the same grid as the float4 path; pcf_add_points (OG.hpp:185 verbatim) equals the oracle's world-frame
+    insertion with an explicit viewpoint."""
+    g = small.grid
+    a, b = pcf.Fusion(g.box, g.res), pcf.Fusion(g.box, g.res)
+    W, H = small.width, small.height
+    for i in range(3):
+        pts, T = small.frame(i)
+        a.push_frame(pts, T, i)
+        step, row = 20, W * 20 + (0 if i == 0 else 12)               # frame 0: dense rows, later frames: padded rows
+        msg = np.zeros(H * row, np.uint8)
+        rows = msg.reshape(H, row)[:, :W * step].reshape(H, W, step)
+        rows[:, :, :12] = pts[:, :3].reshape(H, W, 3).view(np.uint8).reshape(H, W, 12)
+        rows[:, :, 16:20] = 0x7f                                     # rgb bytes: must be ignored
+        b.push_pointcloud2(msg, W, H, step, row, (0, 4, 8), T, i)
+    a.update(); b.update()
+    assert_same(b.extract(), a.extract(), RESULT_FIELDS, "PointCloud2: ")
+    assert_same(b.state(), a.state(), STATE_FIELDS, "PointCloud2 state: ")
+    with pytest.raises(pcf.PcfError):
+        b.push_pointcloud2(np.zeros(64, np.uint8), 2, 1, 18, 36, (0, 4, 8), np.eye(4), 10)   # point_step not a multiple of 4
+    a.close(); b.close()
+
+    og = oracle.OracleGrid(g.box, g.res)
+    fus = pcf.Fusion(g.box, g.res)
+    rng = np.random.default_rng(5)
+    for i in range(3):
+        pts, T = small.frame(i)
+        world = oracle.kat_transform(T, pts[np.isfinite(pts[:, 2])])
+        world[::97, 0] = np.nan                                      # D11: non-finite points are dropped
+        vp = rng.uniform(-1, 1, 3).astype(np.float32)
+        og.add_points_world(world[np.isfinite(world[:, 0])], vp)
+        fus.add_points(np.ascontiguousarray(world), vp, i)
+    og.update(); fus.update()
+    assert_result_parity(fus.extract(), og.download(), "add_points: ")
+    assert_same(fus.state(), og.state(), STATE_FIELDS, "add_points state: ")
+    fus.close()

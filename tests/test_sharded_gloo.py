@@ -95,3 +95,44 @@ def test_frame_blocks_and_slabs():
         assert b[0] == 0 and b[-1] == 500 and all(b[i] <= b[i + 1] for i in range(w))
         loads = [pc[b[i + 1]] - pc[b[i]] for i in range(w)]
         assert sum(loads) == pc[-1] and max(loads) - min(loads) <= 2 * per_plane.max()
+
+
+# ---- exchange v2 (slab-routed records): routing arithmetic over gloo, world_size 2 --------------------------------
+def _worker_v2(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sh, grid, vps, log, n1 = _rank_state(rank, world)
+    plane_cells = n1[1] * n1[2]
+    x = (log[:, 3].view(np.uint32) // plane_cells).astype(np.int64)
+    plane = torch.from_numpy(np.bincount(x, minlength=n1[0]).astype(np.int64))
+    dist.all_reduce(plane)                                      # collective 1: the plane histogram
+    bounds = sh.slab_bounds_from_points(plane.numpy(), world)
+    halo = 3
+    sel = [(x >= max(bounds[d] - halo, 0)) & (x < min(bounds[d + 1] + halo, n1[0])) for d in range(world)]
+    mine = torch.tensor([int(s.sum()) for s in sel], dtype=torch.int64)
+    rows = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(rows, mine)                                 # collective 2: the count matrix
+    off, total = sh.route_offsets(torch.stack(rows).numpy())
+    # the transfer itself (peer stores on the GPU) modelled as every rank contributing its block at its offset
+    recv = [torch.zeros((int(total[d]), 4), dtype=torch.float32) for d in range(world)]
+    for d in range(world):
+        recv[d][off[rank][d]: off[rank][d] + int(mine[d])] = torch.from_numpy(log[sel[d]])
+        dist.all_reduce(recv[d])                                # disjoint blocks: a sum assembles the buffer
+    np.savez(os.path.join(out_dir, f"v2r{rank}.npz"), bounds=np.array(bounds), recv=recv[rank].numpy(), total=total)
+    dist.destroy_process_group()
+
+
+def test_exchange_v2_routing_world2(tmp_path):
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker_v2, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    sh, grid1, vps1, log1, n1 = _rank_state(0, 1)
+    x1 = (log1[:, 3].view(np.uint32) // (n1[1] * n1[2])).astype(np.int64)
+    outs = [np.load(tmp_path / f"v2r{r}.npz") for r in range(world)]
+    b = outs[0]["bounds"]
+    assert np.array_equal(b, outs[1]["bounds"]) and b[0] == 0 and b[-1] == n1[0]
+    for d in range(world):
+        want = log1[(x1 >= max(b[d] - 3, 0)) & (x1 < min(b[d + 1] + 3, n1[0]))]     # slab + halo of the 1-rank log, arrival order
+        assert np.array_equal(outs[d]["recv"].view(np.uint32), want.view(np.uint32))
+    loads = [int(((x1 >= b[d]) & (x1 < b[d + 1])).sum()) for d in range(world)]
+    assert sum(loads) == len(log1) and min(loads) > 0.3 * len(log1)
