@@ -201,11 +201,13 @@ def merge_and_extract_v2(fus, group=None, gather_to=0, peer=None):
     fus.install_records(ptrs[rank], int(total[rank]))
     fus.set_slab(bounds[rank], bounds[rank + 1])
     fus.update()
-    local = fus.extract()
+    local = fus.extract() if gather_to is not None else fus.extract_raw()
     ev[2].record()
     torch.cuda.synchronize(dev)
     timings = {"exchange_ms": ev[0].elapsed_time(ev[1]), "slab_process_ms": ev[1].elapsed_time(ev[2]),
                "records_in": int(total[rank]), "records_out": int(mine.sum().item())}
+    if gather_to is None:                      # every rank keeps (or writes) its own slab: no result traffic at all
+        return local, None, timings
     parts = [None] * world if rank == gather_to else None
     dist.gather_object(local, parts, dst=gather_to, group=group)
     full = _concat_results(parts) if rank == gather_to else None
