@@ -39,6 +39,6 @@ if os.path.exists(rep_path):
                     v = float(r[i].replace(",", "")); u = units[i].lower()
                     return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
                 tr = b(h.index("dram__bytes_read.sum")) + b(h.index("dram__bytes_write.sum"))
-                json.dump({"kernel": "k_ingest<4>", "dram_bytes_per_launch": tr, "source": f"profiles/{tag}_ncu_full_summary.csv (ncu --set full, 100-frame launch)"},
+                json.dump({"kernel": "k_ingest_bulk<16>", "dram_bytes_per_launch": tr, "source": f"profiles/{tag}_ncu_full_summary.csv (ncu --set full, 200-frame launch)"},
                           open(os.path.join(out, "ingest_traffic.json"), "w"))
     print(open(os.path.join(out, f"{tag}_ncu_full_summary.csv")).read())
