@@ -307,10 +307,12 @@ int flush_holders(pcf_ctx* c) {
     return PCF_OK;
 }
 
-// one launch over `nf` equally sized clouds resident in device memory
-int launch_ingest(pcf_ctx* c, const float* pts_dev, uint64_t frame_stride, uint32_t n, uint32_t nf, uint32_t stride,
-                  const double* poses, uint32_t first_frame_idx, const float* explicit_vp = nullptr) {
-    static thread_local IngestBatch b;     // 24 KB of kernel parameters (limit: 32 KB)
+// one launch over `nf` equally sized clouds resident in device memory.  Batch = IngestBatch (up to 256 frames, 24 KB of
+// kernel parameters) or IngestBatch1 (one frame, 144 bytes: the per-frame host path launches 200 times per step).
+template <class Batch>
+int launch_ingest_t(pcf_ctx* c, const float* pts_dev, uint64_t frame_stride, uint32_t n, uint32_t nf, uint32_t stride,
+                    const double* poses, uint32_t first_frame_idx, const float* explicit_vp) {
+    static thread_local Batch b;
     const GridParams& g = c->g;
     uint32_t chunks = div_up(n, kWChunk);
     b.pts = pts_dev;
@@ -325,30 +327,35 @@ int launch_ingest(pcf_ctx* c, const float* pts_dev, uint64_t frame_stride, uint3
     b.vp[3] = 1.f;
     for (uint32_t f = 0; f < nf; f++)
         for (int i = 0; i < 12; i++) b.T[f][i] = poses[(size_t)f * 16 + i];
-    // B200 path: bulk-async ring (needs 16-byte aligned chunks); anything else takes the generic kernel
     if (explicit_vp) {       // pcf_add_points: cloud already in the fusion frame
         dim3 grid(div_up(chunks, kWarps), nf, 1);
-        LAUNCH(c, (k_ingest<0, true>), grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
+        LAUNCH(c, (k_ingest<0, true, Batch>), grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
         CU(cudaGetLastError());
         c->n_chunks += chunks * nf;
         return PCF_OK;
     }
+    // B200 path: bulk-async ring (needs 16-byte aligned chunks); anything else takes the generic kernel
     const bool aligned = ((uintptr_t)pts_dev % 16 == 0) && ((frame_stride * 4) % 16 == 0 || nf == 1);
     const uint32_t total = chunks * nf;
     const uint32_t grid_bulk = std::min<uint32_t>((uint32_t)(c->sm_count * c->ctas_per_sm), div_up(total, kWarps));
     if (c->use_bulk && aligned && stride == 4) {
-        LAUNCH_SMEM(c, (k_ingest_bulk<16, kBulkMinBlocks, kBulkRounds>), grid_bulk, kBlock, kWarps * kWChunk * 16, b, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
+        LAUNCH_SMEM(c, (k_ingest_bulk<16, kBulkMinBlocks, kBulkRounds, 1, Batch>), grid_bulk, kBlock, kWarps * kWChunk * 16, b, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
     } else if (c->use_bulk && aligned && stride == 3 && n % 4 == 0) {
-        LAUNCH_SMEM(c, (k_ingest_bulk<12, kBulkMinBlocks, kBulkRounds>), grid_bulk, kBlock, kWarps * kWChunk * 12, b, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
+        LAUNCH_SMEM(c, (k_ingest_bulk<12, kBulkMinBlocks, kBulkRounds, 1, Batch>), grid_bulk, kBlock, kWarps * kWChunk * 12, b, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
     } else {
         dim3 grid(div_up(chunks, kWarps), nf, 1);
-        if (stride == 4) LAUNCH(c, k_ingest<4>, grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
-        else if (stride == 3) LAUNCH(c, k_ingest<3>, grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
-        else LAUNCH(c, k_ingest<0>, grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
+        if (stride == 4) LAUNCH(c, (k_ingest<4, false, Batch>), grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
+        else if (stride == 3) LAUNCH(c, (k_ingest<3, false, Batch>), grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
+        else LAUNCH(c, (k_ingest<0, false, Batch>), grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
     }
     CU(cudaGetLastError());
     c->n_chunks += chunks * nf;
     return PCF_OK;
+}
+int launch_ingest(pcf_ctx* c, const float* pts_dev, uint64_t frame_stride, uint32_t n, uint32_t nf, uint32_t stride,
+                  const double* poses, uint32_t first_frame_idx, const float* explicit_vp = nullptr) {
+    if (nf == 1) return launch_ingest_t<IngestBatch1>(c, pts_dev, frame_stride, n, nf, stride, poses, first_frame_idx, explicit_vp);
+    return launch_ingest_t<IngestBatch>(c, pts_dev, frame_stride, n, nf, stride, poses, first_frame_idx, explicit_vp);
 }
 
 int check_frame_idx(pcf_ctx* c, uint32_t first, uint32_t count) {
@@ -443,7 +450,12 @@ int run_scoring(pcf_ctx* c) {
     ScoreOut so{(float4*)c->sc_a.p, (float4*)c->sc_b.p, (float*)c->sc_c.p};
     uint32_t* fault = (uint32_t*)c->total_dev.p + 8;
     CU(cudaMemsetAsync(fault, 0, 32, c->stream));
-    LAUNCH(c, k_score, div_up(nn, 128), 128, (const uint32_t*)c->n_cell.p, (const float4*)c->n_nrm.p, (const uint32_t*)c->n_mark.p, nn,
+    // canonical schedule: one update pass that saw every point currently in the log
+    const bool simple = c->marks.size() == 1 && c->marks[0] == c->n_chunks * (uint32_t)kWChunk && !c->holder;
+    if (simple) LAUNCH(c, k_score<true>, div_up(nn, 128), 128, (const uint32_t*)c->n_cell.p, (const float4*)c->n_nrm.p, (const uint32_t*)c->n_mark.p, nn,
+           c->g, c->occ_bits, c->occ_rank, (const uint32_t*)c->uv_off.p, (const uint32_t*)c->nidx.p, (const float4*)c->sorted.p,
+           (const uint32_t*)c->holder, so, (uint32_t)c->n_points, (const uint32_t*)c->uv_cell.p, fault);
+    else LAUNCH(c, k_score<false>, div_up(nn, 128), 128, (const uint32_t*)c->n_cell.p, (const float4*)c->n_nrm.p, (const uint32_t*)c->n_mark.p, nn,
            c->g, c->occ_bits, c->occ_rank, (const uint32_t*)c->uv_off.p, (const uint32_t*)c->nidx.p, (const float4*)c->sorted.p,
            (const uint32_t*)c->holder, so, (uint32_t)c->n_points, (const uint32_t*)c->uv_cell.p, fault);
     CU(cudaGetLastError());
@@ -613,8 +625,10 @@ int pcf_create(const pcf_config* cfg, pcf_ctx** out) {
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, PCF_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(PCF_ERR_CUDA); } } while (0)
     CUC(cudaSetDevice(c->device));
     CUC(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
-    CUC(cudaFuncSetAttribute(k_ingest_bulk<16, kBulkMinBlocks, kBulkRounds>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * kWChunk * 16));
-    CUC(cudaFuncSetAttribute(k_ingest_bulk<12, kBulkMinBlocks, kBulkRounds>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * kWChunk * 12));
+    CUC(cudaFuncSetAttribute(k_ingest_bulk<16, kBulkMinBlocks, kBulkRounds, 1, IngestBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * kWChunk * 16));
+    CUC(cudaFuncSetAttribute(k_ingest_bulk<12, kBulkMinBlocks, kBulkRounds, 1, IngestBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * kWChunk * 12));
+    CUC(cudaFuncSetAttribute(k_ingest_bulk<16, kBulkMinBlocks, kBulkRounds, 1, IngestBatch1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * kWChunk * 16));
+    CUC(cudaFuncSetAttribute(k_ingest_bulk<12, kBulkMinBlocks, kBulkRounds, 1, IngestBatch1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * kWChunk * 12));
     {
         const char* t = getenv("PCF_TRACE");
         c->trace = t && atoi(t) > 0;

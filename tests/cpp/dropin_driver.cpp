@@ -8,7 +8,9 @@
 // The drop-in claim is that both builds write byte-identical files; tests/test_dropin_gpu.py checks exactly that.
 // TEST INFRASTRUCTURE: the PCL / Eigen types come from the stand-in headers under oracle/ref_shim/.
 #include <cstdio>
+#include <cstdint>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -73,6 +75,27 @@ int main(int argc, char** argv) {
     fclose(f);
     grid.updateThicknessVectors<6, 3>();
     grid.downloadData(dir + "/test_cloud.pcd", dir + "/meta.csv");                         // node.cpp:395-398
+    // the download variants the node keeps behind `#if 0` (node.cpp:399-437): dumped with their exact float bits
+    {
+        pcl::PointCloud<pcl::PointXYZRGB>::Ptr hq(new pcl::PointCloud<pcl::PointXYZRGB>), cls(new pcl::PointCloud<pcl::PointXYZRGB>),
+            plain(new pcl::PointCloud<pcl::PointXYZRGB>);
+        pcl::PointCloud<pcl::PointXYZRGBNormal>::Ptr nrm(new pcl::PointCloud<pcl::PointXYZRGBNormal>);
+        grid.downloadHQ(hq, 3.0);                                                          // OG.hpp:545-575
+        grid.downloadClassified(cls);                                                      // OG.hpp:514-543
+        grid.download(plain);                                                              // OG.hpp:491-512
+        grid.download(nrm);                                                                // OG.hpp:577-601
+        FILE* o = fopen((dir + "/variants.txt").c_str(), "w");
+        auto bits = [](float v) { uint32_t u; memcpy(&u, &v, 4); return u; };
+        fprintf(o, "hq %zu %u %u\n", hq->points.size(), hq->width, hq->height);
+        for (auto& p : hq->points) fprintf(o, "%08x %08x %08x %d %d %d\n", bits(p.x), bits(p.y), bits(p.z), p.r, p.g, p.b);
+        fprintf(o, "classified %zu\n", cls->points.size());
+        for (auto& p : cls->points) fprintf(o, "%08x %08x %08x %d %d %d\n", bits(p.x), bits(p.y), bits(p.z), p.r, p.g, p.b);
+        fprintf(o, "plain %zu\n", plain->points.size());
+        for (auto& p : plain->points) fprintf(o, "%08x %08x %08x\n", bits(p.x), bits(p.y), bits(p.z));
+        fprintf(o, "normals %zu\n", nrm->points.size());
+        for (auto& p : nrm->points) fprintf(o, "%08x %08x %08x %08x %08x %08x\n", bits(p.x), bits(p.y), bits(p.z), bits(p.normal[0]), bits(p.normal[1]), bits(p.normal[2]));
+        fclose(o);
+    }
     grid.clearVoxels();                                                                    // node.cpp:438
     return 0;
 }

@@ -50,8 +50,8 @@ def _oracle_files(oracle, scene, outdir, update_every=0, frames=None):
     og.write_files(os.path.join(outdir, "test_cloud.pcd"), os.path.join(outdir, "meta.csv"))
 
 
-def _same_files(a, b):
-    for name in ("test_cloud.pcd", "meta.csv"):
+def _same_files(a, b, names=("test_cloud.pcd", "meta.csv")):
+    for name in names:
         x, y = open(os.path.join(a, name), "rb").read(), open(os.path.join(b, name), "rb").read()
         assert len(x) > 1000, name
         assert x == y, f"{name} differs ({len(x)} vs {len(y)} bytes)"
@@ -78,9 +78,10 @@ def test_dropin_header_same_files_as_reference_header(built, sequence, oracle, t
     subprocess.run([DROPIN, seq, str(ours), str(update_every)], check=True, capture_output=True)
     if os.path.exists(DROPIN_REF):      # the reference's own OccupancyGrid.hpp behind the very same driver source
         subprocess.run([DROPIN_REF, seq, str(ref), str(update_every)], check=True, capture_output=True)
+        _same_files(str(ours), str(ref), ("test_cloud.pcd", "meta.csv", "variants.txt"))   # + downloadHQ / Classified / download
     else:                               # no prebuilt reference binary on this box: the restatement stands in
         _oracle_files(oracle, scene, str(ref), update_every)
-    _same_files(str(ours), str(ref))
+        _same_files(str(ours), str(ref))
 
 
 @pytest.mark.gpu
@@ -106,3 +107,22 @@ def test_replay_reset_discards_only_queued_frames(built, sequence, tmp_path):
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["ok"] and line["integrated"] + line["discarded_by_reset"] == scene.n_frames
     assert os.path.getsize(tmp_path / "test_cloud.pcd") > 1000
+
+
+@pytest.mark.gpu
+def test_service_shell_start_stop_semantics(built, sequence, oracle, tmp_path):
+    """start / stop / process through the line-oriented shell (host/pcf_service): clouds published while stopped are
+    dropped (node.cpp:329-331), queued ones keep integrating after stop (node.cpp:369-375), process writes the files,
+    clears the grid (node.cpp:438) and reports success (D8); a second scan after process starts from an empty grid."""
+    scene, seq = sequence
+    script = "play 0 1\nstart\nplay 1 3\nstop\nplay 4 1\ndrain\nstats\nprocess\nstart\nplay 4 2\nstop\nprocess\nstats\nquit\n"
+    r = subprocess.run([os.path.join(HOST, "pcf_service"), seq, "--out", str(tmp_path)], input=script, capture_output=True, text=True, check=True)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{") or l.startswith("success=")]
+    st1, ok1, ok2, st2 = json.loads(lines[0]), lines[1], lines[2], json.loads(lines[3])
+    assert st1 == {"received": 5, "dropped": 2, "integrated": 3, "discarded_by_reset": 0, "updates": 0}
+    assert ok1 == "success=1" and ok2 == "success=1"
+    assert st2["integrated"] == 5 and st2["dropped"] == 2
+    ref = tmp_path / "ref"
+    ref.mkdir()
+    _oracle_files(oracle, scene, str(ref), 0, frames=[4, 5])     # the files on disk are those of the second scan
+    _same_files(str(tmp_path), str(ref))
