@@ -238,3 +238,66 @@ def test_pointcloud2_front_end_and_add_points(pcf, oracle, small):
     assert_result_parity(fus.extract(), og.download(), "add_points: ")
     assert_same(fus.state(), og.state(), STATE_FIELDS, "add_points state: ")
     fus.close()
+
+
+@pytest.mark.parametrize("kind", ["oracle", "ref_ordered"])
+def test_anisotropic_resolution_and_offset_box(pcf, oracle, small, kind):
+    """setResolution(x, y, z) with three different values and the launch-file style box (not centred, zmin = 0): the walk
+    uses xres_ for every axis (OG.hpp:405), dims truncate per axis (OG.hpp:623-625).  Checked against the restatement
+    AND against the reference's own header (oracle/_ref, D3-ordered build) when it is available."""
+    if kind != "oracle" and not oracle.available(kind):
+        pytest.skip("oracle/_ref not built on this box")
+    box = (-0.21, 0.24, -0.2, 0.26, 0.0, 0.23)
+    res = (0.005, 0.004, 0.006)
+    og = oracle.OracleGrid(box, res, kind=kind)
+    fus = pcf.Fusion(box, res)
+    assert fus.dims == og.dims
+    for i in range(small.n_frames):
+        pts, T = small.frame(i)
+        T = T.copy(); T[2, 3] += 0.1          # lift the sphere so that it straddles the z = 0 face of the box
+        fus.push_frame(pts, T, i)
+        og.add_frame(pts, T)
+        if i == 2:
+            fus.update(); og.update()
+    fus.update(); og.update()
+    want = og.download()
+    assert len(want) > 500
+    assert_result_parity(fus.extract(), want, f"anisotropic/{kind} result.")
+    fus.close()
+
+
+def test_error_behaviour(pcf, small):
+    """Errors are status codes with a message, never exceptions across the ABI or silent acceptance."""
+    g = small.grid
+    with pytest.raises(pcf.PcfError, match="k_neighbourhood"):
+        import ctypes as C
+        lib = pcf.load_library()
+        b = importlib_binding(pcf)
+        cfg = b._Config()
+        lib.pcf_default_config(C.byref(cfg))
+        cfg.k_neighbourhood = 3
+        h = C.c_void_p()
+        rc = lib.pcf_create(C.byref(cfg), C.byref(h))
+        assert rc == -1 and not h.value
+        raise pcf.PcfError(rc, lib.pcf_last_error(None).decode())
+    with pytest.raises(pcf.PcfError, match="20-bit|32 bit"):
+        pcf.Fusion((-600.0, 600.0) * 3, 0.001)                       # 1.2e6 cells per axis
+    fus = pcf.Fusion(g.box, g.res)
+    pts, T = small.frame(0)
+    fus.push_frame(pts, T, 5)
+    with pytest.raises(pcf.PcfError, match="does not increase"):
+        fus.push_frame(pts, T, 5)
+    with pytest.raises(pcf.PcfError, match="bad frame arguments"):
+        fus.push_frame(np.zeros((4, 2), np.float32), T, 6)           # stride < 3
+    with pytest.raises(pcf.PcfError, match="max_frames"):
+        fus.push_frame(pts, T, 1 << 20)
+    fus.update()
+    assert len(fus.extract()) >= 0                                   # the context is still usable after the errors
+    with pytest.raises(pcf.PcfError, match="interleaved"):
+        fus.exchange_counts([0, fus.dims[0] + 1])                    # sharded merge after an update pass is refused
+    fus.close()
+
+
+def importlib_binding(pcf):
+    import importlib
+    return importlib.import_module(pcf.__name__ + ".binding")
