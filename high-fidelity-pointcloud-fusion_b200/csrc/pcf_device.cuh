@@ -31,7 +31,11 @@ struct GridParams {
     float clip_lo, clip_hi; // same for the camera-frame depth clip, node.cpp:251
     int32_t dim[3];         // xdim_, ydim_, zdim_
     uint32_t n1[3];         // dim + 1 (allocated cells per axis, OG.hpp:626)
-    uint64_t cells;         // n1[0]*n1[1]*n1[2]
+    uint32_t nzp;           // z stride of the LOGICAL cell index: n1[2] rounded up to 32 (a bitmap word never straddles rows)
+    uint32_t plane_cells;   // n1[1] * nzp: logical cells per x plane
+    uint32_t nb[3];         // 64^3 bricks per axis of the PHYSICAL first-frame grid
+    uint64_t cells;         // logical cells = n1[0] * n1[1] * nzp  (sort keys, bitmaps, x-major order)
+    uint64_t phys_cells;    // nb[0]*nb[1]*nb[2] * 64^3 (allocated first_frame entries)
     float walk_step[7];     // float(i * xres_), i = -3..3  (OG.hpp:405, scalar narrowed before the product)
     int32_t walk_k;
     int32_t min_neighbours;
@@ -189,14 +193,22 @@ PCF_HD void voxel_coords(const GridParams& g, V3 p, int& x, int& y, int& z) {
 PCF_HD bool valid_coord(const GridParams& g, int x, int y, int z) {
     return x >= 0 && y >= 0 && z >= 0 && x < g.dim[0] && y < g.dim[1] && z < g.dim[2];
 }
+// LOGICAL cell index: lexicographic in (x, y, z) -- the reference's scan order (OG.hpp:463-465); sort key, bitmap index
 PCF_HD uint32_t cell_index(const GridParams& g, int x, int y, int z) {
-    return ((uint32_t)x * g.n1[1] + (uint32_t)y) * g.n1[2] + (uint32_t)z;
+    return ((uint32_t)x * g.n1[1] + (uint32_t)y) * g.nzp + (uint32_t)z;
 }
 PCF_HD void cell_coords(const GridParams& g, uint32_t cell, int& x, int& y, int& z) {
-    uint32_t xy = cell / g.n1[2];
-    z = (int)(cell - xy * g.n1[2]);
+    uint32_t xy = cell / g.nzp;
+    z = (int)(cell - xy * g.nzp);
     x = (int)(xy / g.n1[1]);
     y = (int)(xy - (uint32_t)x * g.n1[1]);
+}
+// PHYSICAL index into first_frame: 64^3-cell bricks (1 MB each, z fastest inside a brick).  A surface patch touches a
+// handful of 2 MB pages instead of one page per x plane: with the plain x-major grid the integration kernel ran 2.2x
+// slower on a plate lying in the x-y plane than on the same plate in the y-z plane (TLB misses behind every probe).
+PCF_HD uint32_t phys_index(const GridParams& g, int x, int y, int z) {
+    uint32_t brick = (((uint32_t)x >> 6) * g.nb[1] + ((uint32_t)y >> 6)) * g.nb[2] + ((uint32_t)z >> 6);
+    return (brick << 18) | (((uint32_t)x & 63u) << 12) | (((uint32_t)y & 63u) << 6) | ((uint32_t)z & 63u);
 }
 PCF_HD uint64_t hash_id(int x, int y, int z) {
     return ((uint64_t)x << 40) ^ ((uint64_t)y << 20) ^ (uint64_t)z;

@@ -195,8 +195,14 @@ int build_grid_params(pcf_ctx* c) {
         g.dim[a] = (int)d;                       // truncation, OG.hpp:623-625
         g.n1[a] = (uint32_t)g.dim[a] + 1;
     }
-    g.cells = (uint64_t)g.n1[0] * g.n1[1] * g.n1[2];
-    if (g.cells >= 0xFFFFFFFFull) return fail(c, PCF_ERR_INVALID, "grid has %llu cells; the cell index is 32 bit", (unsigned long long)g.cells);
+    g.nzp = (g.n1[2] + 31u) & ~31u;
+    uint64_t plane = (uint64_t)g.n1[1] * g.nzp;
+    g.cells = (uint64_t)g.n1[0] * plane;
+    for (int a = 0; a < 3; a++) g.nb[a] = (g.n1[a] + 63u) / 64u;
+    g.phys_cells = ((uint64_t)g.nb[0] * g.nb[1] * g.nb[2]) << 18;
+    if (g.cells >= 0xFFFFFFFFull || g.phys_cells >= 0xFFFFFFFFull || plane >= 0xFFFFFFFFull)
+        return fail(c, PCF_ERR_INVALID, "grid has %llu cells; the cell index is 32 bit", (unsigned long long)std::max(g.cells, g.phys_cells));
+    g.plane_cells = (uint32_t)plane;
     g.clip_lo = thr_lo(cfg.clip_zmin);
     g.clip_hi = thr_hi(cfg.clip_zmax);
     g.walk_k = cfg.walk_k;
@@ -277,7 +283,7 @@ int build_occupancy(pcf_ctx* c) {
     int rc = reserve(c, c->tmpA, (size_t)c->n_words * 4);
     if (rc) return rc;
     uint32_t* pop = (uint32_t*)c->tmpA.p;
-    LAUNCH(c, k_cells_to_bits, div_up(c->n_words, kBlock), kBlock, c->first_frame, c->g.cells, c->occ_bits, pop, c->n_words);
+    LAUNCH(c, k_cells_to_bits, div_up(c->n_words, kBlock), kBlock, c->first_frame, c->g, c->occ_bits, pop, c->n_words);
     uint32_t* tot = (uint32_t*)c->total_dev.p;
     rc = scan_u32(c, pop, c->occ_rank, c->n_words, tot);
     if (rc) return rc;
@@ -562,7 +568,7 @@ void destroy_impl(pcf_ctx* c) {
 }
 
 int reset_grid_state(pcf_ctx* c) {
-    LAUNCH(c, k_fill_u32, 148 * 8, 512, c->first_frame, c->g.cells, kEmpty);
+    LAUNCH(c, k_fill_u32, 148 * 8, 512, c->first_frame, c->g.phys_cells, kEmpty);
     CU(cudaMemsetAsync(c->nrm_bits, 0, (c->n_words + 2) * 4, c->stream));
     CU(cudaMemsetAsync(c->occ_bits, 0, (c->n_words + 2) * 4, c->stream));
     CU(cudaMemsetAsync(c->vp_table, 0, (size_t)c->cfg.max_frames * sizeof(float4), c->stream));
@@ -638,7 +644,7 @@ int pcf_create(const pcf_config* cfg, pcf_ctx** out) {
     CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     c->n_words = (c->g.cells + 31) / 32;
-    CUC(cudaMalloc(&c->first_frame, c->g.cells * 4));
+    CUC(cudaMalloc(&c->first_frame, c->g.phys_cells * 4));
     CUC(cudaMalloc(&c->nrm_bits, (c->n_words + 2) * 4));
     CUC(cudaMalloc(&c->occ_bits, (c->n_words + 2) * 4));
     CUC(cudaMalloc(&c->occ_rank, (c->n_words + 2) * 4));
@@ -853,7 +859,7 @@ int pcf_update(pcf_ctx* c) {
         if ((rc = reserve(c, c->tmpB, (size_t)c->n_words * 4))) return rc;
         uint32_t* cnt = (uint32_t*)c->tmpA.p;
         uint32_t* off = (uint32_t*)c->tmpB.p;
-        const uint64_t plane = (uint64_t)c->g.n1[1] * c->g.n1[2];
+        const uint64_t plane = (uint64_t)c->g.plane_cells;
         const uint64_t cell_lo = c->slab_hi < 0 ? 0 : (uint64_t)c->slab_lo * plane;
         const uint64_t cell_hi = c->slab_hi < 0 ? c->g.cells : std::min<uint64_t>(c->g.cells, (uint64_t)c->slab_hi * plane);
         LAUNCH(c, k_cand_count, div_up(c->n_words, kBlock), kBlock, c->occ_bits, c->nrm_bits, c->n_words, cell_lo, cell_hi, cnt);
@@ -983,7 +989,7 @@ void* pcf_stream(pcf_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int pcf_grid_buffer(pcf_ctx* c, void** first_frame_dev, uint64_t* n_cells) {
     if (!c || !first_frame_dev || !n_cells) return PCF_ERR_INVALID;
     *first_frame_dev = c->first_frame;
-    *n_cells = c->g.cells;
+    *n_cells = c->g.phys_cells;      // bricked physical layout: identical on every rank, so an elementwise reduce is still valid
     c->occ_dirty = true;        // the caller is about to reduce into it
     c->sorted_valid = false;
     return PCF_OK;
@@ -1037,7 +1043,7 @@ int pcf_log_replace(pcf_ctx* c, const void* log_dev, uint64_t n_points) {
     CU(cudaStreamSynchronize(c->copy_stream));
     const float4* in = (const float4*)log_dev;
     // keep the records of this context's x-slab plus the reach of the +-K walk (OG.hpp:403-405): walk_k cells
-    const uint64_t plane = (uint64_t)c->g.n1[1] * c->g.n1[2];
+    const uint64_t plane = (uint64_t)c->g.plane_cells;
     uint64_t cell_lo = 0, cell_hi = c->g.cells;
     if (c->slab_hi >= 0) {
         int64_t lo = (int64_t)c->slab_lo - c->g.walk_k, hi = (int64_t)c->slab_hi + c->g.walk_k;
@@ -1079,7 +1085,7 @@ int pcf_plane_counts(pcf_ctx* c, uint32_t* counts_host) {
     if (rc) return rc;
     uint32_t np = c->g.n1[0];
     if ((rc = reserve(c, c->tmpA, ((size_t)np + 1) * 4))) return rc;
-    LAUNCH(c, k_plane_counts, div_up(np + 1, kBlock), kBlock, c->occ_bits, c->occ_rank, np, (uint64_t)c->g.n1[1] * c->g.n1[2], c->n_vox,
+    LAUNCH(c, k_plane_counts, div_up(np + 1, kBlock), kBlock, c->occ_bits, c->occ_rank, np, (uint64_t)c->g.plane_cells, c->n_vox,
            (uint32_t*)c->tmpA.p);
     CU(cudaMemcpyAsync(counts_host, c->tmpA.p, ((size_t)np + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -1097,7 +1103,7 @@ int pcf_plane_point_counts(pcf_ctx* c, uint32_t* counts_host) {
     CU(cudaMemsetAsync(c->tmpA.p, 0, (size_t)np * 4, c->stream));
     if (c->n_chunks) {
         uint32_t grid = std::min<uint32_t>(div_up(c->n_chunks, kWarps), (uint32_t)c->sm_count * 4);
-        k_plane_point_counts<<<grid, kBlock, (size_t)np * 4, c->stream>>>(c->log, c->chunk_count, c->n_chunks, c->g.n1[1] * c->g.n1[2], np, (uint32_t*)c->tmpA.p);
+        k_plane_point_counts<<<grid, kBlock, (size_t)np * 4, c->stream>>>(c->log, c->chunk_count, c->n_chunks, c->g.plane_cells, np, (uint32_t*)c->tmpA.p);
         c->stats.kernel_launches++;
         CU(cudaGetLastError());
     }
@@ -1114,7 +1120,7 @@ int pcf_exchange_counts(pcf_ctx* c, const int32_t* bounds, int32_t n_ranks, uint
     const int32_t halo = std::max(c->g.walk_k, 2);      // +-K walk (OG.hpp:403-405) and the 5x5x5 scan (OG.hpp:334)
     ExchangePlan& p = c->plan;
     p.n_ranks = (uint32_t)n_ranks;
-    p.plane_cells = c->g.n1[1] * c->g.n1[2];
+    p.plane_cells = c->g.plane_cells;
     for (int d = 0; d < n_ranks; d++) {
         if (bounds[d] < 0 || bounds[d] > bounds[d + 1] || (uint32_t)bounds[d + 1] > c->g.n1[0]) return fail(c, PCF_ERR_INVALID, "bad slab bounds");
         bool empty = bounds[d] == bounds[d + 1];
@@ -1215,7 +1221,7 @@ int pcf_install_records(pcf_ctx* c, const void* records_dev, uint64_t n) {
     c->n_chunks = 0;                       // the local log is superseded by the routed records (own ones included)
     int rc = ensure_log(c, std::max<uint32_t>(chunks, 1));
     if (rc) return rc;
-    LAUNCH(c, k_fill_u32, 148 * 8, 512, c->first_frame, c->g.cells, kEmpty);
+    LAUNCH(c, k_fill_u32, 148 * 8, 512, c->first_frame, c->g.phys_cells, kEmpty);
     if (n) {
         LAUNCH(c, k_install_records, div_up(n, kBlock), kBlock, (const float4*)records_dev, n, c->g, c->first_frame, c->log);
         LAUNCH(c, k_chunk_counts_dense, div_up(chunks, kBlock), kBlock, c->chunk_count, chunks, n);

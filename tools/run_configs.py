@@ -43,6 +43,7 @@ def run_scene(name, scene, n_frames, batch, update_every=0, oracle=False, frames
 
 
 _CTX = {}
+_PREMUL = None     # optional fixed transform applied to every pose after the clouds were generated (layout experiments)
 
 
 def _run_scene(name, scene, n_frames, batch, update_every, oracle, frames_per_gen, keep=None, numpy_frames=False):
@@ -69,6 +70,8 @@ def _run_scene(name, scene, n_frames, batch, update_every, oracle, frames_per_ge
             dev = torch.from_numpy(frames).cuda()
         else:
             dev, poses = synth.frames_on_device(scene, done, nb)
+        if _PREMUL is not None:
+            poses = np.stack([_PREMUL @ T for T in poses])
         b = 0
         while b < nb:
             k = min(batch, nb - b)
@@ -175,6 +178,12 @@ def main():
             line = run_scene(f"C3 sweep{a.c3_frames}", synth.plate_sweep(a.c3_frames), a.c3_frames, 250, oracle=False, frames_per_gen=250)
         elif c == "C4":
             line = run_scene("C4 hires50", synth.hires_sphere(50), 50, 10, update_every=10, oracle=False, frames_per_gen=10)
+        elif c.startswith("C3x"):       # C3x200: C3 with the fusion frame rotated so that the plate lies in the y-z plane
+            nfr = int(c[3:])            # (layout experiment: the same points land in few x-planes of the x-major grid)
+            global _PREMUL
+            _PREMUL = np.array([[0, 0, 1, 0], [0, 1, 0, 0], [-1, 0, 0, 0], [0, 0, 0, 1]], dtype=np.float64)
+            line = run_scene(f"C3 sweep rotated ({nfr} frames)", synth.plate_sweep(1000), nfr, 250, oracle=False, frames_per_gen=250)
+            _PREMUL = None
         elif c.startswith("C3n"):       # C3n100: the C3 scene cut to 100 frames
             nfr = int(c[3:])
             line = run_scene(f"C3 sweep ({nfr} frames)", synth.plate_sweep(1000), nfr, 250, oracle=False, frames_per_gen=250)
