@@ -65,6 +65,8 @@ def rank_views(fus, device):
 
 
 def _finish_rank(fus, merged_log, slab):
+    # libpcfusion works on its own CUDA stream: everything torch produced for it (copies, cat, collectives) must be complete
+    torch.cuda.synchronize(torch.device("cuda", fus.device_index))
     fus.set_slab(slab[0], slab[1])
     fus.log_replace(merged_log, merged_log.shape[0])
     fus.update()
@@ -142,6 +144,7 @@ def merge_and_extract_local_v2(ranks):
     for r, (f, d) in enumerate(zip(ranks, devs)):
         vp, nf = f.viewpoint_table()
         _as_tensor(vp, (nf, 4), "<f4", d).copy_(vps.to(d))
+        torch.cuda.synchronize(d)
         f.install_records(bufs[r], int(total[r]))
         f.set_slab(bounds[r], bounds[r + 1])
         f.update()
@@ -189,6 +192,7 @@ def merge_and_extract_v2(fus, group=None, gather_to=0, peer=None):
     bounds = slab_bounds_from_points(plane.cpu().numpy(), world)
     vp, nf = fus.viewpoint_table()
     dist.all_reduce(_as_tensor(vp, (nf, 4), "<f4", dev), group=group)
+    torch.cuda.synchronize(dev)               # the library reads the table on its own stream
     mine = torch.from_numpy(fus.exchange_counts(bounds).astype(np.int64)).to(dev)
     rows = [torch.zeros_like(mine) for _ in range(world)]
     dist.all_gather(rows, mine, group=group)

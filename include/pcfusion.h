@@ -133,8 +133,10 @@ void pcf_host_free(void* p);
 int pcf_upload_ticket(pcf_ctx* ctx, uint64_t* ticket);
 int pcf_wait_upload(pcf_ctx* ctx, uint64_t ticket);
 /* Same for clouds already resident in device memory: n_frames clouds of n_per_frame points each, back to
- * back, integrated by ONE launch.  poses: n_frames x 16 doubles (host).  Frames get indices
- * first_frame_idx .. first_frame_idx+n_frames-1. */
+ * back, integrated by ONE launch (up to 256 frames per launch; longer batches are split).  poses: n_frames x 16
+ * doubles (host).  Frames get indices first_frame_idx .. first_frame_idx+n_frames-1.  The kernel runs on the context's
+ * own stream (pcf_stream): the clouds must be complete when this is called (synchronise the stream that produced them,
+ * or make pcf_stream wait on it), and must stay valid until pcf_sync. */
 int pcf_push_frames_device(pcf_ctx* ctx, const float* pts_dev, uint32_t n_frames, uint32_t n_per_frame,
                            uint32_t stride_floats, const double* poses, uint32_t first_frame_idx);
 int pcf_sync(pcf_ctx* ctx);     /* wait for all queued integration work */
