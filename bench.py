@@ -311,7 +311,7 @@ def run_b200(args):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"kernel": "k_ingest<4,true>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"kernel": "k_ingest_bulk<16>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_step / launches_per_step, "launch_ms": per_launch_ms,
                 "kept_fraction": kept / points_per_step}

@@ -84,7 +84,7 @@ struct pcf_ctx {
     uint64_t uploads = 0;                 // ticket of the most recent host push
 
     // scratch
-    DevBuf scan1, scan2, tmpA, tmpB, tmpC, tmpD, hist, keysA, keysB, valsA, valsB, sorted, uv_cell, uv_off, nidx,
+    DevBuf scan1, scan2, tmpA, tmpB, tmpC, tmpD, hist, sort_tab, keysA, keysB, valsA, valsB, sorted, uv_cell, uv_off, nidx,
         sc_a, sc_b, sc_c, flags, slots, cand, res_dev, total_dev;
     uint32_t* total_host = nullptr;       // pinned, 4 words
     // host results (pinned)
@@ -410,28 +410,44 @@ int prepare_sorted(pcf_ctx* c) {
 
     int bits = 1;
     while ((1ull << bits) < c->g.cells) bits++;
-    int passes = (bits + 7) / 8;
-    int per = (bits + passes - 1) / passes;
-    uint32_t mask = (1u << per) - 1;
-    uint32_t tiles_later = div_up(P, kChunk);
-    uint32_t tiles_log = div_up(c->n_chunks, kWarps);
-    if ((rc = reserve(c, c->hist, (size_t)256 * std::max(tiles_log, tiles_later) * 4))) return rc;
+    // pass M: the top digit, straight from the log; then local LSD passes over the remaining low bits inside each bucket
+    const int msd_bits = std::min(8, bits), rem = bits - msd_bits;
+    const int lp = (rem + 7) / 8, per = lp ? (rem + lp - 1) / lp : 0;
+    const uint32_t tiles_m = div_up(c->n_chunks, kWarps);
+    const uint32_t tiles_max = div_up(P, kChunk) + 256;              // every bucket may end with a partial tile
+    if ((rc = reserve(c, c->hist, (size_t)256 * std::max(tiles_m, tiles_max) * 4))) return rc;
+    if ((rc = reserve(c, c->sort_tab, (size_t)tiles_max * sizeof(SortTile) + 2 * 257 * 4))) return rc;
     uint32_t* hist = (uint32_t*)c->hist.p;
+    SortTile* tab = (SortTile*)c->sort_tab.p;
+    uint32_t* bucket_start = (uint32_t*)(tab + tiles_max);
+    uint32_t* tile_base = bucket_start + 257;
     uint32_t *kin = nullptr, *vin = nullptr, *kout = (uint32_t*)c->keysA.p, *vout = (uint32_t*)c->valsA.p;
-    for (int p = 0; p < passes; p++) {
+    {
         SortSrc src{};
-        src.log = c->log; src.chunk_count = c->chunk_count; src.keys = kin; src.vals = vin; src.n = P; src.n_chunks = c->n_chunks;
-        uint32_t shift = (uint32_t)(p * per);
-        uint32_t nt = p == 0 ? tiles_log : tiles_later;
-        if (p == 0) LAUNCH(c, k_sort_hist<true>, nt, kBlock, src, nt, shift, mask, hist);
-        else LAUNCH(c, k_sort_hist<false>, nt, kBlock, src, nt, shift, mask, hist);
-        rc = scan_u32(c, hist, hist, (uint64_t)256 * nt, nullptr);
-        if (rc) return rc;
-        if (p == 0) LAUNCH(c, k_sort_scatter<true>, nt, kBlock, src, nt, shift, mask, hist, kout, vout);
-        else LAUNCH(c, k_sort_scatter<false>, nt, kBlock, src, nt, shift, mask, hist, kout, vout);
+        src.log = c->log; src.chunk_count = c->chunk_count; src.n_chunks = c->n_chunks; src.n_tiles = tiles_m;
+        const uint32_t mask = (1u << msd_bits) - 1;
+        LAUNCH(c, k_sort_hist<true>, tiles_m, kBlock, src, (uint32_t)rem, mask, hist);
+        if ((rc = scan_u32(c, hist, hist, (uint64_t)256 * tiles_m, nullptr))) return rc;
+        LAUNCH(c, k_sort_scatter<true>, tiles_m, kBlock, src, (uint32_t)rem, mask, hist, kout, vout);
         kin = kout; vin = vout;
-        kout = (kin == (uint32_t*)c->keysA.p) ? (uint32_t*)c->keysB.p : (uint32_t*)c->keysA.p;
-        vout = (vin == (uint32_t*)c->valsA.p) ? (uint32_t*)c->valsB.p : (uint32_t*)c->valsA.p;
+        kout = (uint32_t*)c->keysB.p; vout = (uint32_t*)c->valsB.p;
+    }
+    if (lp > 0) {
+        LAUNCH(c, k_sort_bucket_tiles, 1, 256, (const uint32_t*)hist, tiles_m, 1u << msd_bits, P, bucket_start, tile_base);
+        uint32_t n_tiles = 0;
+        if ((rc = read_total(c, tile_base + 256, &n_tiles))) return rc;
+        LAUNCH(c, k_sort_tile_table, div_up(std::max<uint32_t>(n_tiles, 1), kBlock), kBlock, (const uint32_t*)bucket_start, (const uint32_t*)tile_base, tab);
+        for (int p = 0; p < lp; p++) {
+            SortSrc src{};
+            src.keys = kin; src.vals = vin; src.tab = tab; src.n_tiles_dev = tile_base + 256;
+            const uint32_t shift = (uint32_t)(p * per), mask = (1u << per) - 1;   // a last digit reaching into the top digit is constant inside a bucket
+            LAUNCH(c, k_sort_hist<false>, n_tiles, kBlock, src, shift, mask, hist);
+            if ((rc = scan_u32(c, hist, hist, (uint64_t)256 * n_tiles, nullptr))) return rc;
+            LAUNCH(c, k_sort_scatter<false>, n_tiles, kBlock, src, shift, mask, hist, kout, vout);
+            kin = kout; vin = vout;
+            kout = (kin == (uint32_t*)c->keysA.p) ? (uint32_t*)c->keysB.p : (uint32_t*)c->keysA.p;
+            vout = (vin == (uint32_t*)c->valsA.p) ? (uint32_t*)c->valsB.p : (uint32_t*)c->valsA.p;
+        }
     }
     LAUNCH(c, k_gather_points, div_up(P, kBlock), kBlock, c->log, vin, (uint64_t)P, (float4*)c->sorted.p);
     LAUNCH(c, k_segment_heads, div_up(P, kBlock), kBlock, kin, (uint64_t)P, c->occ_bits, c->occ_rank, (uint32_t*)c->uv_cell.p,
@@ -544,7 +560,7 @@ void destroy_impl(pcf_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
-    DevBuf* bufs[] = {&c->n_cell, &c->n_nrm, &c->n_mark, &c->scan1, &c->scan2, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->hist,
+    DevBuf* bufs[] = {&c->n_cell, &c->n_nrm, &c->n_mark, &c->scan1, &c->scan2, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->hist, &c->sort_tab,
                       &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->sorted, &c->uv_cell, &c->uv_off, &c->nidx, &c->sc_a, &c->sc_b,
                       &c->sc_c, &c->flags, &c->slots, &c->cand, &c->res_dev, &c->total_dev, &c->dense_log};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
