@@ -50,7 +50,7 @@ ABI_SYMBOLS = [
     "pcf_extract_hq", "pcf_clear", "pcf_dump_state", "pcf_get_stats", "pcf_reset_stats", "pcf_last_timings", "pcf_stream",
     "pcf_grid_buffer", "pcf_viewpoint_table", "pcf_log_compact", "pcf_log_replace", "pcf_set_slab", "pcf_plane_counts", "pcf_plane_point_counts", "pcf_exchange_counts", "pcf_exchange_scatter", "pcf_recv_buffer", "pcf_ipc_export", "pcf_ipc_open",
     "pcf_ipc_close_all", "pcf_install_records", "pcf_kat_transform_voxel",
-    "pcf_kat_normal", "pcf_kat_score",
+    "pcf_kat_normal", "pcf_kat_score", "pcf_kat_format_float",
 ]
 
 _lib = None
@@ -111,6 +111,7 @@ def load_library():
     lib.pcf_ipc_close_all.argtypes = [vp]
     lib.pcf_install_records.argtypes = [vp, vp, C.c_uint64]
     lib.pcf_kat_transform_voxel.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
+    lib.pcf_kat_format_float.argtypes = [C.c_float, C.c_int, C.c_char_p]
     lib.pcf_kat_normal.argtypes = [vp, vp, C.c_uint32, vp]
     lib.pcf_kat_score.argtypes = [vp, vp, C.c_uint32, vp, vp, vp, vp, vp, vp, vp]
     _lib = lib

@@ -204,6 +204,7 @@ int pcf_install_records(pcf_ctx* ctx, const void* records_dev, uint64_t n_record
 int pcf_kat_transform_voxel(pcf_ctx* ctx, const float* pts_host, uint32_t n, uint32_t stride_floats,
                             const double pose[16], float* world_xyz, int32_t* ijk, uint8_t* kept);
 int pcf_kat_normal(pcf_ctx* ctx, const float* xyz_host, uint32_t n_points, float* normal3);
+int pcf_kat_format_float(float v, int precision, char* out32);   /* the writer's float formatting (6 = CSV %g, 8 = PCD %.8g) */
 int pcf_kat_score(pcf_ctx* ctx, const float* xyz_host, uint32_t n_points, const float axis_pt[3],
                   const float normal[3], float* centroid3, float* sd3, float* mean_dist, float* sd_dist,
                   int32_t* count);

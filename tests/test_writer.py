@@ -56,3 +56,21 @@ def test_special_values(pcf, tmp_path):
     pts = (tmp_path / "c.pcd").read_text().splitlines()[11:]
     assert pts[0] == "0 0 0 4278190080 0 0 1 0"
     assert pts[1] == "nan 9.9999997e-10 -123456.79 4278190080 0.57735026 -0.57735026 0.57735026 0"
+
+
+def test_float_formatting_equals_printf(pcf):
+    """std::to_chars(general, precision) in the writer == printf %g / %.8g (what ostream << float and PCL's ASCII writer emit)
+    over random bit patterns, denormals, powers of ten, rounding boundaries and the special values."""
+    lib = pcf.load_library()
+    rng = np.random.default_rng(11)
+    vals = [rng.integers(0, 2**32, 150000, dtype=np.uint64).astype(np.uint32).view(np.float32),
+            (rng.normal(size=50000) * 10.0 ** rng.integers(-12, 9, 50000)).astype(np.float32),
+            np.array([0.0, -0.0, 1.0, -1.0, 1e-5, 1e-4, 9.9999995e-5, 0.0001, 123456.5, 1234567.0, 999999.5, 999999.44, 1e6, 1e7, 99999999.0,
+                      1e8, 0.5, 0.15, 1.17549435e-38, 1e-45, 3.4028235e38, np.inf, -np.inf, 0.000512345678, 2.5e-7, 1e-10], np.float32)]
+    buf = C.create_string_buffer(64)
+    for v in np.concatenate(vals):
+        for prec, fmt in ((6, "%g"), (8, "%.8g")):
+            n = lib.pcf_kat_format_float(C.c_float(float(v)), prec, buf)
+            got = buf.value[:n].decode()
+            want = "nan" if np.isnan(v) else fmt % float(v)
+            assert got == want, (float(v), prec, got, want)
