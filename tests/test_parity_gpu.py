@@ -301,3 +301,46 @@ def test_error_behaviour(pcf, small):
 def importlib_binding(pcf):
     import importlib
     return importlib.import_module(pcf.__name__ + ".binding")
+
+
+def test_edge_cases_empty_ragged_unaligned(pcf, oracle, small, tmp_path):
+    """Empty clouds, 1-point clouds, lengths around the 256-point chunk size, all-NaN and all-outside clouds, packed xyz
+    with a length that is not a multiple of 4 and a cloud that starts at an odd float offset (generic kernel instead of the
+    bulk-copy one): the grid and the extraction must equal the oracle's; an empty grid extracts nothing and process()
+    writes header-only files."""
+    g = small.grid
+    fus, og = pcf.Fusion(g.box, g.res), oracle.OracleGrid(g.box, g.res)
+    assert len(fus.extract()) == 0                                   # nothing integrated yet
+    fus.process(str(tmp_path / "empty.pcd"), str(tmp_path / "empty.csv"))
+    assert (tmp_path / "empty.csv").read_text().count("\n") == 1 and "POINTS 0" in (tmp_path / "empty.pcd").read_text()
+    pts, T = small.frame(0)
+    fid = 0
+
+    def both(cloud, pose):
+        nonlocal fid
+        fus.push_frame(cloud, pose, fid)
+        og.add_frame(np.ascontiguousarray(cloud[:, :3]) if cloud.shape[1] != 4 else cloud, pose)
+        fid += 1
+
+    ok = np.isfinite(pts[:, 2])
+    valid = pts[ok]
+    both(np.zeros((0, 4), np.float32), T)                            # empty
+    for n in (1, 255, 256, 257, 513):
+        both(np.ascontiguousarray(valid[:n]), T)                     # ragged lengths
+    both(np.full((300, 4), np.nan, np.float32), T)                   # all NaN
+    far = valid[:300].copy(); far[:, :3] *= 50.0
+    both(far, T)                                                     # all clipped / outside the box
+    both(np.ascontiguousarray(valid[:1001, :3]), T)                  # packed xyz, n % 4 != 0 -> generic kernel
+    both(np.ascontiguousarray(valid[:1000, :3]), T)                  # packed xyz, bulk-copy path
+    backing = np.zeros(4 * len(valid) + 1, np.float32)
+    odd = backing[1:].reshape(-1, 4)                                 # 4-byte aligned only
+    odd[:] = valid
+    both(odd, T)
+    for i in range(1, small.n_frames):                               # enough surface for normals to appear
+        both(*small.frame(i))
+    fus.update(); og.update()
+    assert_same(fus.state(), og.state(), STATE_FIELDS, "edge state.")
+    want = og.download()
+    assert len(want) > 100
+    assert_result_parity(fus.extract(), want, "edge result.")
+    fus.close()
