@@ -170,7 +170,7 @@ void* pcf_stream(pcf_ctx* ctx);
 /* ---- multi-GPU merge hooks (one context per GPU; the exchange itself is the caller's, e.g. NCCL) --------
  * Frames are sharded over ranks in contiguous frame_idx blocks.  At process() the dense first-frame grid is
  * min-reduced across ranks, viewpoints are all-gathered, and each rank's point log is exchanged. */
-int pcf_grid_buffer(pcf_ctx* ctx, void** first_frame_dev, uint64_t* n_cells);    /* uint32 per cell, 0x7FFFFFFF = empty */
+int pcf_grid_buffer(pcf_ctx* ctx, void** first_frame_dev, uint64_t* n_cells);    /* uint32 per cell, 0x7FFFFFFF = empty; bricked physical order, the same on every rank with the same config: reduce it elementwise */
 int pcf_viewpoint_table(pcf_ctx* ctx, void** vp_dev, uint32_t* max_frames);       /* float4 per frame_idx, w=1 when set */
 int pcf_log_compact(pcf_ctx* ctx, void** log_dev, uint64_t* n_points);            /* float4 (x,y,z,cell) in arrival order */
 /* x-slab [x_lo, x_hi) of voxels this context normal-estimates, scores and extracts (x_hi < 0: whole grid).  The
