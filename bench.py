@@ -296,6 +296,25 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = points_per_step * world * args.steps / float(t.item())
+    # informational: the same leg with packed xyz clouds (12 B/point instead of the float4 layout's 16): PCIe is the bound
+    e2e_packed = None
+    if world == 1:
+        host3 = torch.from_numpy(np.ascontiguousarray(frames[:, :, :3])).pin_memory()
+        def ingest_host3():
+            for i in range(N_FRAMES):
+                fus.push_frame(host3[i], poses[i], first + i)
+            return fus.count_kept()
+        ingest_host3(); process_and_clear()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            ingest_host3()
+            if s + 1 < args.steps:
+                fus.clear()
+        e2e_packed = {"value": points_per_step * args.steps / (time.perf_counter() - t0), "unit": "points/s",
+                      "h2d_bytes_per_step": int(points_per_step * 12), "note": "packed xyz host clouds (stride 3); clear() between steps inside the timed region"}
+        process_and_clear()
+        del host3
     clocks = sampler.stop()
 
     # ---- roofline of the dominant kernel (k_ingest) -----------------------------------------------------------
@@ -336,6 +355,7 @@ def run_b200(args):
             "step_wall_ms": 1e3 * t_wall / args.steps,
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(points_per_step * 16),
                     "d2h_bytes_per_step": 4, "process_wall_ms": statistics.mean(e2e_proc)},
+            "e2e_packed_xyz": e2e_packed,
             "ingest_ms_per_rank": [x / args.steps for x in per_rank_ms],
             "gpu_launches": int(st["kernel_launches"]),
             "clocks": clocks, "roofline": roofline, "gen_s": t_gen,
