@@ -101,6 +101,15 @@ class OccupancyGrid {
         return !(p(0) >= xmax_ || p(1) >= ymax_ || p(2) >= zmax_ || p(0) <= xmin_ || p(1) <= ymin_ || p(2) <= zmin_);
     }
     bool validCoord(int x, int y, int z) const { return x >= 0 && y >= 0 && z >= 0 && x < xdim_ && y < ydim_ && z < zdim_; }
+    // OG.hpp:131-135: double arithmetic narrowed to float; returns any 3-float type constructible from (x, y, z)
+    template <class Vec3>
+    Vec3 getVoxelCenter(int x, int y, int z) const {
+        return Vec3(xmin_ + xres_ * (x) + xres_ / 2.0, ymin_ + yres_ * (y) + yres_ / 2.0, zmin_ + zres_ * (z) + zres_ / 2.0);
+    }
+    // dims without a device (construct() needs one): xdim_ = (int)((xmax_ - xmin_) / xres_) etc., OG.hpp:623-625
+    void computeDims() {
+        xdim_ = (int)((xmax_ - xmin_) / xres_); ydim_ = (int)((ymax_ - ymin_) / yres_); zdim_ = (int)((zmax_ - zmin_) / zres_);
+    }
 
     // OG.hpp:185-280.  `cloud` is in the fusion frame (the node transformed it, node.cpp:289); `viewpoint` is the
     // camera position.  N (OpenMP threads in the reference, whose pragmas are commented out) is ignored.

@@ -69,6 +69,17 @@ def test_host_builds_and_fails_loudly_without_gpu(built, sequence, tmp_path):
     assert not os.path.exists(tmp_path / "test_cloud.pcd")
 
 
+def test_dropin_coordinate_helpers_equal_reference_header(built):
+    """CPU: getVoxelCoords / getHashId / validPoints / validCoord / getVoxelCenter / dims of the drop-in class against the
+    reference's own header behind the same source (tests/cpp/helpers_check.cpp), 60 000 points incl. cell borders."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "helpers_ref")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/helpers_ref not built (needs /root/reference)")
+    a = subprocess.run([os.path.join(ROOT, "tests", "_build", "helpers_b200")], capture_output=True, check=True).stdout
+    b = subprocess.run([ref], capture_output=True, check=True).stdout
+    assert len(a) > 1_000_000 and a == b
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("update_every", [0, 2])
 def test_dropin_header_same_files_as_reference_header(built, sequence, oracle, tmp_path, update_every):
