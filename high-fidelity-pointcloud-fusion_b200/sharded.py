@@ -168,6 +168,7 @@ class PeerExchange:
         dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.group)
         if self.ptrs is None or int(need.item()):
             self.fus.ipc_close_all()
+            dist.barrier(group=self.group)     # no rank may free its exported buffer while a peer still has it mapped
             self.cap = max(int(my_total) + int(my_total) // 4, 1 << 16, self.cap)   # head-room: the next process() rarely re-maps
             mine = self.fus.recv_buffer(self.cap)
             handles = [None] * self.world
