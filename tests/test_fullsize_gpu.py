@@ -128,3 +128,27 @@ def test_c5_sheets_world_points_bit_exact_vs_oracle(pcf, oracle):
     assert_result_parity(fus.extract(), want, "C5 result.")
     assert_same(fus.state(), og.state(), STATE_FIELDS, "C5 state.")
     fus.close()
+
+
+def test_c4_resolution_interleaved_bit_exact_on_a_small_box(pcf, oracle):
+    """C4's ingredients -- 1920x1080 clouds, 0.5 mm voxels, an update between frames -- on a box small enough for the oracle's
+    dense CPU grid (a 4 cm sphere in a 12 cm box: 240^3 cells): bit-exact state and extraction."""
+    synth = _synth(pcf)
+    scene = synth.sphere_turntable(6, 1920, 1080, 0.0005, fx=1800.0, radius=0.04, standoff=0.36, box_half=0.06)
+    g = scene.grid
+    fus, og = pcf.Fusion(g.box, g.res), oracle.OracleGrid(g.box, g.res)
+    assert fus.dims == og.dims == (239, 239, 239)
+    kept = 0
+    for i in range(scene.n_frames):
+        pts, T = scene.frame(i)
+        fus.push_frame(pts, T, i)
+        kept += og.add_frame(pts, T)
+        if i in (1, 3):
+            fus.update(); og.update()
+    assert fus.count_kept() == kept and kept > 300000
+    fus.update(); og.update()
+    want = og.download()
+    assert len(want) > 50000
+    assert_result_parity(fus.extract(), want, "C4-small result.")
+    assert_same(fus.state(), og.state(), STATE_FIELDS, "C4-small state.")
+    fus.close()
