@@ -344,3 +344,40 @@ def test_edge_cases_empty_ragged_unaligned(pcf, oracle, small, tmp_path):
     assert len(want) > 100
     assert_result_parity(fus.extract(), want, "edge result.")
     fus.close()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_randomised_scenes_and_schedules(pcf, oracle, seed):
+    """Seeded fuzzing of the whole path: random sphere size / stand-off / image size / resolution (anisotropic in half of the
+    cases) / box offset / number of frames / update schedule (updates after random frames, sometimes twice in a row, sometimes
+    none before the end) -- state and extraction bit-exact against the oracle every time."""
+    synth = _synth(pcf)
+    rng = np.random.default_rng(1000 + seed)
+    radius = float(rng.uniform(0.06, 0.16))
+    standoff = float(rng.uniform(0.30 + radius, 0.58))          # keeps the visible cap inside the 0.28-0.6 m depth clip
+    w, h = int(rng.choice([96, 160, 200])), int(rng.choice([72, 120, 150]))
+    res0 = float(rng.choice([0.003, 0.004, 0.005, 0.0065]))
+    n_frames = int(rng.integers(3, 9))
+    scene = synth.sphere_turntable(n_frames, w, h, res0, radius=radius, standoff=standoff, box_half=radius + 0.05,
+                                   noise_sigma=float(rng.uniform(0.0002, 0.001)))
+    off = rng.uniform(-0.02, 0.02, 3)
+    half = radius + 0.05
+    box = (-half + off[0], half + off[0], -half + off[1], half + off[1], -half * float(rng.uniform(0.3, 1.0)) + off[2], half + off[2])
+    res = (res0, res0, res0) if seed % 2 == 0 else tuple(float(res0 * f) for f in rng.uniform(0.8, 1.25, 3))
+    fus, og = pcf.Fusion(box, res), oracle.OracleGrid(box, res)
+    assert fus.dims == og.dims
+    updates = set(int(i) for i in rng.choice(n_frames, size=int(rng.integers(0, n_frames)), replace=False))
+    for i in range(n_frames):
+        pts, T = scene.frame(i)
+        if rng.random() < 0.3:                                   # ragged: drop a random tail of the cloud
+            pts = np.ascontiguousarray(pts[: int(rng.integers(1, len(pts)))])
+        fus.push_frame(pts, T, i)
+        og.add_frame(pts, T)
+        if i in updates:
+            fus.update(); og.update()
+            if rng.random() < 0.25:
+                fus.update(); og.update()                        # a second pass with no new frames in between
+    fus.update(); og.update()
+    assert_same(fus.state(), og.state(), STATE_FIELDS, f"fuzz {seed} state.")
+    assert_result_parity(fus.extract(), og.download(), f"fuzz {seed} result.")
+    fus.close()
