@@ -346,7 +346,7 @@ def test_edge_cases_empty_ragged_unaligned(pcf, oracle, small, tmp_path):
     fus.close()
 
 
-@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("PCF_FUZZ_SEEDS", "16"))))
 def test_randomised_scenes_and_schedules(pcf, oracle, seed):
     """Seeded fuzzing of the whole path: random sphere size / stand-off / image size / resolution (anisotropic in half of the
     cases) / box offset / number of frames / update schedule (updates after random frames, sometimes twice in a row, sometimes
