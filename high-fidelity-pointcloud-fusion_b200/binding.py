@@ -49,7 +49,7 @@ ABI_SYMBOLS = [
     "pcf_push_frame", "pcf_push_pointcloud2", "pcf_add_points", "pcf_host_alloc", "pcf_host_free", "pcf_upload_ticket", "pcf_wait_upload", "pcf_push_frames_device", "pcf_sync", "pcf_count_kept", "pcf_update", "pcf_extract", "pcf_process", "pcf_write_result",
     "pcf_extract_hq", "pcf_clear", "pcf_dump_state", "pcf_get_stats", "pcf_reset_stats", "pcf_last_timings", "pcf_stream",
     "pcf_grid_buffer", "pcf_viewpoint_table", "pcf_log_compact", "pcf_log_replace", "pcf_set_slab", "pcf_plane_counts", "pcf_plane_point_counts", "pcf_exchange_counts", "pcf_exchange_scatter", "pcf_recv_buffer", "pcf_ipc_export", "pcf_ipc_open",
-    "pcf_ipc_close_all", "pcf_install_records", "pcf_kat_transform_voxel",
+    "pcf_ipc_close_all", "pcf_install_records", "pcf_get_viewpoints", "pcf_set_viewpoints", "pcf_enable_peer_access", "pcf_kat_transform_voxel",
     "pcf_kat_normal", "pcf_kat_score", "pcf_kat_format_float",
 ]
 
@@ -110,6 +110,9 @@ def load_library():
     lib.pcf_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
     lib.pcf_ipc_close_all.argtypes = [vp]
     lib.pcf_install_records.argtypes = [vp, vp, C.c_uint64]
+    lib.pcf_get_viewpoints.argtypes = [vp, vp, C.c_uint32, C.c_uint32]
+    lib.pcf_set_viewpoints.argtypes = [vp, vp, C.c_uint32, C.c_uint32]
+    lib.pcf_enable_peer_access.argtypes = [vp, C.c_int32]
     lib.pcf_kat_transform_voxel.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
     lib.pcf_kat_format_float.argtypes = [C.c_float, C.c_int, C.c_char_p]
     lib.pcf_kat_normal.argtypes = [vp, vp, C.c_uint32, vp]

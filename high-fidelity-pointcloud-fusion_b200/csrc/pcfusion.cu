@@ -1226,6 +1226,33 @@ int pcf_ipc_close_all(pcf_ctx* c) {
     return PCF_OK;
 }
 
+int pcf_get_viewpoints(pcf_ctx* c, float* host4, uint32_t first, uint32_t count) {
+    if (!c || !host4 || (uint64_t)first + count > c->cfg.max_frames) return PCF_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(host4, c->vp_table + first, (size_t)count * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return PCF_OK;
+}
+int pcf_set_viewpoints(pcf_ctx* c, const float* host4, uint32_t first, uint32_t count) {
+    if (!c || !host4 || (uint64_t)first + count > c->cfg.max_frames) return PCF_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(c->vp_table + first, host4, (size_t)count * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return PCF_OK;
+}
+int pcf_enable_peer_access(pcf_ctx* c, int32_t peer_device) {
+    if (!c) return PCF_ERR_INVALID;
+    if (peer_device == c->device) return PCF_OK;
+    CU(cudaSetDevice(c->device));
+    int can = 0;
+    CU(cudaDeviceCanAccessPeer(&can, c->device, peer_device));
+    if (!can) return fail(c, PCF_ERR_INVALID, "device %d cannot access device %d directly", c->device, peer_device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+    if (e != cudaSuccess) return fail(c, PCF_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d) failed: %s", peer_device, cudaGetErrorString(e));
+    return PCF_OK;
+}
+
 int pcf_install_records(pcf_ctx* c, const void* records_dev, uint64_t n) {
     if (!c || (!records_dev && n)) return PCF_ERR_INVALID;
     if (n >= 0xFFFFFFFFull) return fail(c, PCF_ERR_CAPACITY, "merged log too large");

@@ -199,6 +199,12 @@ int pcf_ipc_export(pcf_ctx* ctx, void* handle64);                          /* cu
 int pcf_ipc_open(pcf_ctx* ctx, const void* handle64, void** peer_ptr);
 int pcf_ipc_close_all(pcf_ctx* ctx);
 int pcf_install_records(pcf_ctx* ctx, const void* records_dev, uint64_t n_records);
+/* Helpers for a host that drives several contexts from ONE process (host/pcf_replay --gpus N): rows [first, first+count)
+ * of the viewpoint table as 4 floats per frame (x, y, z, 1 when set), and peer access from this context's device to
+ * `peer_device` so that pcf_exchange_scatter may store into another context's receive buffer directly. */
+int pcf_get_viewpoints(pcf_ctx* ctx, float* host4, uint32_t first, uint32_t count);
+int pcf_set_viewpoints(pcf_ctx* ctx, const float* host4, uint32_t first, uint32_t count);
+int pcf_enable_peer_access(pcf_ctx* ctx, int32_t peer_device);
 
 /* ---- known-answer hooks: run ONE device function over an array (tests bit-compare with the oracle) ---- */
 int pcf_kat_transform_voxel(pcf_ctx* ctx, const float* pts_host, uint32_t n, uint32_t stride_floats,

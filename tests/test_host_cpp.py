@@ -137,3 +137,24 @@ def test_service_shell_start_stop_semantics(built, sequence, oracle, tmp_path):
     ref.mkdir()
     _oracle_files(oracle, scene, str(ref), 0, frames=[4, 5])     # the files on disk are those of the second scan
     _same_files(str(tmp_path), str(ref))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("devices", ["0,0,0", "0,1"])
+def test_replay_sharded_in_one_process_matches_oracle(built, sequence, oracle, tmp_path, devices):
+    """host/pcf_replay --gpus N: N contexts of ONE C++ process, frames in contiguous blocks, exchange v2 driven from C++
+    (host/sharded_fusion.cpp; no NCCL, no Python) -> the same files as the oracle fed every frame.  "0,0,0" = three contexts
+    on one GPU; "0,1" = two real GPUs with peer access (skipped on a single-GPU box)."""
+    import torch
+    devs = [int(d) for d in devices.split(",")]
+    if max(devs) >= torch.cuda.device_count():
+        pytest.skip("needs %d GPUs" % (max(devs) + 1))
+    scene, seq = sequence
+    ours, ref = tmp_path / "ours", tmp_path / "ref"
+    ours.mkdir(); ref.mkdir()
+    r = subprocess.run([REPLAY, seq, "--out", str(ours), "--gpus", str(len(devs)), "--devices", devices], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["ok"] and line["gpus"] == len(devs) and line["frames"] == scene.n_frames and line["kernel_launches"] > 0
+    _oracle_files(oracle, scene, str(ref), 0)
+    _same_files(str(ours), str(ref))
