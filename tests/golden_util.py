@@ -15,7 +15,9 @@ def fixtures():
 
 def load(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
-    fx = types.SimpleNamespace(name=name, box=tuple(z["box"]), res=float(z["res"]), clip=tuple(z["clip"]), frames=z["frames"],
+    res = z["res"]
+    res = float(res) if res.ndim == 0 else tuple(float(r) for r in res)
+    fx = types.SimpleNamespace(name=name, box=tuple(z["box"]), res=res, clip=tuple(z["clip"]), frames=z["frames"],
                                poses=z["poses"], schedules=[int(s) for s in z["schedules"]], dims=tuple(int(d) for d in z["dims"]))
     fx.result = {s: types.SimpleNamespace(**{f: z[f"res{s}_{f}"] for f in RES_F}) for s in fx.schedules}
     fx.state = {s: types.SimpleNamespace(**{f: z[f"state{s}_{f}"] for f in STATE_F}) for s in fx.schedules}

@@ -37,11 +37,13 @@ def same(a, b, fields):
     return all(np.array_equal(getattr(a, f).view(np.uint8), getattr(b, f).view(np.uint8)) for f in fields)
 
 
-def make(name, scene, every_list):
+def make(name, scene, every_list, grid=None, pose_premul=None):
+    """grid: override of the scene's GridSpec (e.g. anisotropic resolution, offset box); pose_premul: rigid motion applied to
+    every pose after the clouds were generated (moves the whole scene in the fusion frame)."""
     frames = [np.ascontiguousarray(scene.frame(i)[0][:, :3]) for i in range(scene.n_frames)]
-    poses = [scene.pose(i) for i in range(scene.n_frames)]
-    g = scene.grid
-    out = {"box": np.array(g.box, np.float64), "res": np.float32(g.res), "clip": np.array([g.clip_zmin, g.clip_zmax]),
+    poses = [scene.pose(i) if pose_premul is None else pose_premul @ scene.pose(i) for i in range(scene.n_frames)]
+    g = grid or scene.grid
+    out = {"box": np.array(g.box, np.float64), "res": np.asarray(g.res, np.float32), "clip": np.array([g.clip_zmin, g.clip_zmax]),
            "frames": np.stack(frames), "poses": np.stack(poses), "schedules": np.array(every_list, np.int32)}
     for every in every_list:
         r_ref, s_ref, dims = run("ref_ordered", g, frames, poses, every)
@@ -66,3 +68,8 @@ if __name__ == "__main__":
     make("sphere_5mm", synth.sphere_turntable(5, 120, 90, 0.005, noise_sigma=0.0006), [0, 1, 2])
     # finer voxels, denser pixels: long per-voxel buffers, many in-cylinder points
     make("sphere_2mm", synth.sphere_turntable(4, 200, 150, 0.002, radius=0.06, standoff=0.36, box_half=0.1, noise_sigma=0.0003), [0, 2])
+    # launch-file style grid: three different resolutions (the walk uses xres_ on every axis, OG.hpp:405), a box that is not
+    # centred and whose z = 0 face cuts the (lifted) sphere; update after every frame and after every third frame
+    lift = np.eye(4); lift[:3, 3] = [0.013, -0.008, 0.09]
+    make("sphere_aniso", synth.sphere_turntable(6, 120, 90, 0.005, noise_sigma=0.0006), [0, 1, 3],
+         grid=synth.GridSpec((-0.21, 0.24, -0.2, 0.26, 0.0, 0.23), (0.005, 0.004, 0.006)), pose_premul=lift)
