@@ -11,7 +11,6 @@ import json
 import os
 import subprocess
 
-import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,7 +1,6 @@
 """CPU known-answer tests of the oracle's building blocks, each against a hand-derivable value or an independent
 numpy evaluation of the reference formula (file:line in the oracle source)."""
 import numpy as np
-import pytest
 
 
 def test_dims_truncation_quirk(oracle):

@@ -3,7 +3,7 @@ NVLink peer stores) must give the same bytes as one GPU fed every frame.  Rank 0
 import importlib, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-import numpy as np, torch, torch.distributed as dist
+import torch, torch.distributed as dist
 import pcfusion_b200 as pcf
 from helpers import RESULT_FIELDS, bits_equal
 sh = importlib.import_module("high-fidelity-pointcloud-fusion_b200.sharded")

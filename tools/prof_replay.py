@@ -3,7 +3,7 @@ PROF_VARIANTS="A=1,B=2;C=3" runs the replay once per ';'-separated environment s
 ncu capture can compare library variants."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 import bench
 import pcfusion_b200 as pcf
 n = int(os.environ.get("PROF_FRAMES", "200"))
