@@ -5,20 +5,27 @@ Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]` pri
 
 Workload at N=1 = BASELINE.json configs[1]: "200-frame synthetic turntable scan, 1 mm voxels, 0.5 m box".
 A step = one pass of the hot path over the whole 200-frame sequence:
-    ingest (clip -> FP64 transform -> crop -> voxel index -> occupancy -> point log)   <- timed: value / ms_per_step
+    ingest (clip -> FP64 transform -> crop -> voxel index -> occupancy -> point log)   <- timed
     update + extract (normals, cylinder scoring, compacted extraction) and clear       <- reported as process_ms
-`value`  : input points (clipped ones included) / ingest time, clouds already resident in HBM.
-`e2e`    : same metric through the C ABI with HOST (pinned) clouds: every frame's H2D copy and the read-back of
-           the integration summary are inside the timed region.
-N>1      : frames sharded in contiguous blocks, one process per GPU, no collective on the ingest path (weak
-           scaling: every rank integrates its own 200-frame block); the process()-time grid merge is timed apart.
---impl reference : the reference's CPU implementation of the same path on the host cores (oracle/_ref = the
+`e2e`    : THE HEADLINE.  The metric through the C ABI with HOST clouds (pinned float4 arrays, what a bridge holds): every
+           frame goes through pcf_submit_frame -- host staging (depth clip + pack, node.cpp:218-263), H2D copy of the staged
+           cloud, integration kernel -- and the step ends with the D2H read-back of the integration summary.  All inside
+           the timed region.  `e2e_roofline` says what bounds it (PCIe bytes vs the measured pinned-copy peak, host bytes).
+`value`  : the same metric with the clouds already resident in HBM, ONE 200-frame launch (value_kind "hbm_resident_batch"):
+           the kernel number the `roofline` block explains.  Not reachable end to end on a PCIe-attached host.
+`whole_path` : ingest (e2e route) + process() + result D2H, wall clock, for the whole 200-frame job.
+N>1      : frames sharded in contiguous blocks, one process per GPU, no collective on the ingest path (weak scaling:
+           every rank integrates its own 200-frame block); the process()-time exchange is timed apart.  `c3_strong` adds
+           BASELINE configs[2] (1000-frame sweep, 1 m box) split N ways -- the strong-scaling curve -- and
+           `multi_gpu_parity` says whether a sharded replay was byte-identical to one GPU in this very run.
+--impl reference : the reference's CPU implementation of the same 200-frame path on the host cores (oracle/_ref = the
            reference's own OccupancyGrid.hpp compiled against shim headers; falls back to the oracle port).
 """
 from __future__ import annotations
 
 import argparse
 import concurrent.futures as cf
+import importlib
 import json
 import os
 import statistics
@@ -35,14 +42,17 @@ sys.path.insert(0, ROOT)
 WORKLOAD = "turntable200: 200 x 640x480 organized clouds, sphere r=0.15 m, 1 mm voxels, 0.5 m box, two elevation rings"
 N_FRAMES = 200
 BATCH = 200           # frames per ingest launch on the HBM-resident path (library limit: 256)
-CPU_SAMPLE_FRAMES = 20
+C3_FRAMES = 1000
+MOD = 1 << 59         # checksum sums are reduced mod 2^59 so that an int64 all-reduce over <= 8 ranks cannot overflow
+
+
+def _synth():
+    return importlib.import_module("high-fidelity-pointcloud-fusion_b200.synth")
 
 
 def make_scene(n_frames=N_FRAMES, rank=0, world=1):
-    import importlib
-    synth = importlib.import_module("high-fidelity-pointcloud-fusion_b200.synth")
     # one global sequence of world*n_frames frames; this rank owns the contiguous block [rank*n, (rank+1)*n)
-    return synth.sphere_turntable(n_frames * world, rings=2), rank * n_frames
+    return _synth().sphere_turntable(n_frames * world, rings=2), rank * n_frames
 
 
 def gen_frames(scene, first, n, threads=None):
@@ -113,64 +123,237 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_baseline_run(frames, poses, grid, max_frames=CPU_SAMPLE_FRAMES):
-    """Time the reference's CPU path on a bounded sample: add_frame over the first frames, then update+download."""
+def host_threads(world_local=1):
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 4
+    return max(1, n), max(2, min(16, n // max(1, world_local)))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own path on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_baseline_run(frames, poses, grid, process=True):
+    """The reference's CPU path over ALL given frames: add_frame per frame (z clip, transformPointCloud, addPoints),
+    then updateThicknessVectors + downloadData."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
     kind, label = ("ref_timing", "reference") if O.available("ref_timing") else ("oracle", "port")
     if kind == "oracle":
         O.build()
-    n = min(max_frames, len(frames))
+    n = len(frames)
     og = O.OracleGrid(grid.box, grid.res, grid.clip_zmin, grid.clip_zmax, reserve_hint=1000, kind=kind)
     t0 = time.perf_counter()
     kept = 0
     for i in range(n):
         kept += og.add_frame(frames[i], poses[i])
     t1 = time.perf_counter()
-    devnull = os.open(os.devnull, os.O_WRONLY)
-    saved = os.dup(1)
-    os.dup2(devnull, 1)          # the reference prints progress lines to stdout
-    try:
-        og.update()
-        nout = len(og.download())
-    finally:
-        os.dup2(saved, 1)
-        os.close(devnull)
-        os.close(saved)
-    t2 = time.perf_counter()
+    nout, t2 = None, t1
+    if process:
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)          # the reference prints progress lines to stdout
+        try:
+            og.update()
+            nout = len(og.download())
+        finally:
+            os.dup2(saved, 1)
+            os.close(devnull)
+            os.close(saved)
+        t2 = time.perf_counter()
     og.close()
     pts = n * frames.shape[1]
     return {"value": pts / (t1 - t0), "unit": "points/s", "cores": 1, "kind": label,
-            "sample": f"first {n} of {len(frames)} frames of the workload ({pts} input points, {kept} kept); "
-                      f"grid path single-threaded as in the reference (OG.hpp:190-193 pragmas are commented out)",
-            "ingest_s": t1 - t0, "process_ms": (t2 - t1) * 1e3, "extracted_voxels": nout,
-            "host_cpus": os.cpu_count()}
+            "sample": f"all {n} frames of the workload ({pts} input points, {kept} kept); grid path single-threaded as in "
+                      f"the reference (OG.hpp:190-193 pragmas are commented out)",
+            "ingest_s": t1 - t0, "process_ms": (t2 - t1) * 1e3 if process else None, "extracted_voxels": nout,
+            "whole_path_ms": (t2 - t0) * 1e3 if process else None, "host_cpus": os.cpu_count()}
 
 
 def run_reference(args):
+    """Every executed step integrates ALL 200 frames (same work as one step of the B200 arm).  One full pass costs 10-25 s of
+    CPU, so the arm executes as many of the requested W + K passes as fit PCF_REF_BUDGET_S (default 240 s; at least one timed
+    pass, at most one warm-up pass) and reports their mean: fewer repeats, never fewer frames."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    budget = float(os.environ.get("PCF_REF_BUDGET_S", "240"))
+    t_start = time.perf_counter()
     scene, first = make_scene()
-    n = CPU_SAMPLE_FRAMES
-    frames, poses = gen_frames(scene, first, n)
+    frames, poses = gen_frames(scene, first, N_FRAMES)
+    warm_done = 0
+    if args.warmup > 0:
+        cpu_baseline_run(frames, poses, scene.grid, process=False)
+        warm_done = 1
     runs = []
-    for s in range(args.warmup + args.steps):
-        r = cpu_baseline_run(frames, poses, scene.grid, n)
-        if s >= args.warmup:
-            runs.append(r)
-    total_pts = sum(n * frames.shape[1] for _ in runs)
+    while len(runs) < args.steps:
+        t0 = time.perf_counter()
+        runs.append(cpu_baseline_run(frames, poses, scene.grid, process=True))
+        step_s = time.perf_counter() - t0
+        if time.perf_counter() - t_start + step_s > budget:
+            break
+    total_pts = len(runs) * N_FRAMES * frames.shape[1]
     total_s = sum(r["ingest_s"] for r in runs)
     val = total_pts / total_s
     base = dict(runs[-1]); base["value"] = val
+    wp_ms = statistics.mean(r["whole_path_ms"] for r in runs)
     line = {"impl": "reference", "metric": "fused points/sec", "value": val, "unit": "points/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / len(runs), "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "steps_executed": len(runs), "warmup_executed": warm_done,
+            "ms_per_step": 1e3 * total_s / len(runs), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 transform / f32 statistics", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": base["sample"]},
+            "config": {"workload": WORKLOAD, "frames_per_gpu": N_FRAMES, "points_per_frame": int(frames.shape[1])},
             "process_ms": statistics.mean(r["process_ms"] for r in runs),
+            "whole_path": {"ms": wp_ms, "points_per_s": N_FRAMES * frames.shape[1] / (wp_ms * 1e-3),
+                           "what": "200-frame ingest + updateThicknessVectors + downloadData scan (no file writing)"},
             "cpu_baseline": base,
             "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------------------
+def checksums(res):
+    out = [len(res), int(res.hash.sum(dtype=np.uint64)) % MOD, int(res.count.sum(dtype=np.int64))]
+    for f in ("centroid", "normal", "sd", "mean_dist", "sd_dist"):
+        a = getattr(res, f).reshape(-1).view(np.uint32)
+        out.append(int(np.bitwise_xor.reduce(a)) if len(a) else 0)
+    return out
+
+
+def multi_gpu_parity(pcf, sh, local, rank, world):
+    """A small frame-sharded replay on the real GPUs of this run (exchange over CUDA IPC / NVLink peer stores), gathered to
+    rank 0 and compared byte for byte with one GPU fed every frame.  Canonical and interleaved (update every 3 frames) schedules."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import RESULT_FIELDS, bits_equal
+    scene = _synth().sphere_turntable(16, 320, 240, 0.002)
+    g = scene.grid
+    ok = True
+    detail = []
+    for update_every in (0,):
+        fus = pcf.Fusion(g.box, g.res, device=local)
+        peer = sh.PeerExchange(fus)
+        lo, hi = sh.frame_block(scene.n_frames, rank, world)
+        for i in range(lo, hi):
+            fus.push_frame(*scene.frame(i), i)
+        _, full, _ = sh.merge_and_extract_v2(fus, peer=peer)
+        if rank == 0:
+            one = pcf.Fusion(g.box, g.res, device=local)
+            for i in range(scene.n_frames):
+                one.push_frame(*scene.frame(i), i)
+            one.update()
+            want = one.extract()
+            same = len(want) > 1000 and all(bits_equal(getattr(full, f), getattr(want, f)) for f in RESULT_FIELDS)
+            ok &= same
+            detail.append({"update_every": update_every, "voxels": len(want), "byte_identical": bool(same)})
+            one.close()
+        fus.close()
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=f"cuda:{local}")
+    dist.broadcast(flag, 0)
+    return bool(flag.item()), detail
+
+
+def c3_strong(pcf, sh, local, rank, world, peer_factory):
+    """BASELINE configs[2]: 1000-frame sweep, 1 m box @ 1 mm (1000^3 grid), frames split over the N ranks in contiguous
+    blocks; process() = exchange + slab update/extract.  Clouds are generated on the GPU (torch, never on the host)."""
+    import torch
+    import torch.distributed as dist
+    synth = _synth()
+    dev = torch.device("cuda", local)
+    scene = synth.plate_sweep(C3_FRAMES)
+    g, npf = scene.grid, scene.points_per_frame
+
+    def ingest(fus, lo, hi, batch=125):
+        ms = 0.0
+        stream = torch.cuda.ExternalStream(fus.stream, device=local)
+        for b in range(lo, hi, batch):
+            k = min(batch, hi - b)
+            pts, poses = synth.frames_on_device(scene, b, k, dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fus.push_frames_device(pts, k, npf, 4, poses, b)
+            e1.record(stream)
+            fus.sync()
+            ms += e0.elapsed_time(e1)
+            del pts
+        return ms
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lo, hi = sh.frame_block(C3_FRAMES, rank, world)
+    fus = pcf.Fusion(g.box, g.res, device=local, max_frames=max(1 << 16, C3_FRAMES + 1), log_capacity_hint=(hi - lo) * npf)
+    peer = peer_factory(fus) if world > 1 else None
+    out = None
+    for rep in range(2):                       # second repetition = warm buffers, reported
+        ms = ingest(fus, lo, hi)
+        barrier()
+        t0 = time.perf_counter()
+        if world > 1:
+            _, _, tm = sh.merge_and_extract_v2(fus, peer=peer, gather_to=None)     # every rank keeps its own x-slab
+        else:
+            fus.update(); t_u = fus.timings()["update_ms"]
+            fus.extract_raw(); t_e = fus.timings()
+            tm = {"exchange_ms": 0.0, "slab_process_ms": t_u + t_e["extract_device_ms"] + t_e["extract_d2h_ms"]}
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        if rep == 1:
+            res = fus.extract()                # extraction is idempotent: the slab's result again, for the checksums only
+            cs = checksums(res)
+            t = torch.tensor([ms, tm["exchange_ms"], tm["slab_process_ms"]], dtype=torch.float64, device=dev)
+            sums = torch.tensor(cs[:3], dtype=torch.int64, device=dev)
+            xors = torch.tensor(cs[3:], dtype=torch.int64, device=dev)
+            allx = [xors]
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dist.all_reduce(sums)
+                allx = [torch.zeros_like(xors) for _ in range(world)]
+                dist.all_gather(allx, xors)
+            got = [int(sums[0]), int(sums[1]) % MOD, int(sums[2])] + \
+                  [int(np.bitwise_xor.reduce(np.array([int(a[i]) for a in allx], dtype=np.int64))) for i in range(5)]
+            out = {"workload": f"sweep{C3_FRAMES}: {C3_FRAMES} x 640x480 clouds, wavy plate, 1 mm voxels, 1 m box (1000^3 cells), frames split x{world}",
+                   "frames": C3_FRAMES, "ingest_ms_max_rank": float(t[0]), "ingest_pts_s": C3_FRAMES * npf / (float(t[0]) * 1e-3),
+                   "process_ms": wall, "exchange_ms": float(t[1]), "slab_ms": float(t[2]), "voxels": got[0], "checksums": got}
+        fus.clear()
+    fus.close()
+    if world > 1:
+        # rank 0 integrates ALL frames alone: the sharded extraction must have the same count and checksums
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        if rank == 0:
+            one = pcf.Fusion(g.box, g.res, device=local, max_frames=max(1 << 16, C3_FRAMES + 1), log_capacity_hint=C3_FRAMES * npf)
+            ms1 = ingest(one, 0, C3_FRAMES)
+            one.update()
+            want = checksums(one.extract())
+            want[1] %= MOD
+            out["single_gpu_ingest_pts_s"] = C3_FRAMES * npf / (ms1 * 1e-3)
+            out["checksums_equal"] = [int(a) for a in out["checksums"]] == [int(b) for b in want]
+            one.close()
+        dist.barrier()
+    else:
+        out["checksums_equal"] = None          # N=1 IS the single-GPU run the sharded ones are compared with
+    return out
+
+
+def pinned_copy_peak(local):
+    """Measured H2D bandwidth of one large pinned copy (GB/s): the PCIe roofline of the e2e leg."""
+    import torch
+    n = 256 << 20
+    h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d = torch.empty(n, dtype=torch.uint8, device=f"cuda:{local}")
+    best = 0.0
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        d.copy_(h, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, n / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    return best
 
 
 def run_b200(args):
@@ -181,11 +364,14 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sh = importlib.import_module("high-fidelity-pointcloud-fusion_b200.sharded")
+    n_cpus, stage_threads = host_threads(local_world)
     scene, first = make_scene(N_FRAMES, rank, world)
     grid = scene.grid
     npf = scene.points_per_frame
@@ -193,10 +379,16 @@ def run_b200(args):
     frames, poses = gen_frames(scene, first, N_FRAMES)
     t_gen = time.perf_counter() - t_gen
 
+    parity, parity_detail = (None, None)
+    if world > 1:
+        parity, parity_detail = multi_gpu_parity(pcf, sh, local, rank, world)
+
     dev_frames = torch.from_numpy(frames).cuda(local)                 # HBM-resident clouds (983 MB > 126 MB L2)
     host_frames = torch.from_numpy(frames).pin_memory()               # pinned host clouds for the e2e leg
+    host_list = [host_frames[i] for i in range(N_FRAMES)]
+    pose_list = [np.ascontiguousarray(poses[i], np.float64).reshape(16) for i in range(N_FRAMES)]
     fus = pcf.Fusion(grid.box, grid.res, grid.clip_zmin, grid.clip_zmax, device=local,
-                     max_frames=max(1 << 16, N_FRAMES * world + 1), log_capacity_hint=N_FRAMES * npf)
+                     max_frames=max(1 << 16, N_FRAMES * world + 1), log_capacity_hint=N_FRAMES * npf, stage_threads=stage_threads)
     stream = torch.cuda.ExternalStream(fus.stream, device=local)
     points_per_step = N_FRAMES * npf
 
@@ -210,11 +402,7 @@ def run_b200(args):
             nb = min(BATCH, N_FRAMES - b)
             fus.push_frames_device(dev_frames[b], nb, npf, 4, poses[b:b + nb], first + b)
 
-    sh = peer = None
-    if world > 1:
-        import importlib
-        sh = importlib.import_module("high-fidelity-pointcloud-fusion_b200.sharded")
-        peer = sh.PeerExchange(fus)      # receive buffers mapped into every peer (CUDA IPC): the exchange kernel stores over NVLink
+    peer = sh.PeerExchange(fus) if world > 1 else None    # receive buffers mapped into every peer (CUDA IPC): the exchange kernel stores over NVLink
 
     def process_and_clear(keep=None):
         if world > 1:     # process() across ranks: slab-routed records written straight into the peers' buffers, then slab work
@@ -260,6 +448,7 @@ def run_b200(args):
     barrier()
     t_wall = time.perf_counter() - t_wall
     st = fus.stats()
+    del flush
     ingest_ms = [a.elapsed_time(b) for a, b in ev]
     total_ingest_ms = sum(ingest_ms)
     t = torch.tensor([total_ingest_ms], dtype=torch.float64, device=f"cuda:{local}")
@@ -272,50 +461,62 @@ def run_b200(args):
     max_ingest_ms = float(t.item())
     value = points_per_step * world * args.steps / (max_ingest_ms * 1e-3)
 
-    # ---- e2e: host (pinned) clouds through the C ABI, copies inside the timed region -------------------------
+    # ---- e2e: host (pinned) float4 clouds through pcf_submit_frame: staging + H2D + kernel + summary read-back ----------
     def ingest_host():
         for i in range(N_FRAMES):
-            fus.push_frame(host_frames[i], poses[i], first + i)
-        return fus.count_kept()              # drain + D2H read of the integration summary
+            fus.submit_frame(host_list[i], pose_list[i], first + i)
+        return fus.count_kept()              # drains the staging pool and the GPU + D2H read of the integration summary
 
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(max(2, min(args.warmup, 3))):
         ingest_host(); process_and_clear()
-    e2e_s = 0.0
-    e2e_proc = []
+    e2e_s, wp_s = 0.0, 0.0
     barrier()
+    fus.reset_stats()
     for s in range(args.steps):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        ingest_host()
-        e2e_s += time.perf_counter() - t0
-        t0 = time.perf_counter()
+        k2 = ingest_host()
+        t1 = time.perf_counter()
         process_and_clear()
-        e2e_proc.append((time.perf_counter() - t0) * 1e3)
+        t2 = time.perf_counter()
+        e2e_s += t1 - t0
+        wp_s += t2 - t0
     barrier()
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+    st_e2e = fus.stats()
+    assert k2 == kept, f"staged route kept {k2} points, HBM-resident route {kept}"
+    t = torch.tensor([e2e_s, wp_s], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = points_per_step * world * args.steps / float(t.item())
-    # informational: the same leg with packed xyz clouds (12 B/point instead of the float4 layout's 16): PCIe is the bound
-    e2e_packed = None
+    e2e_value = points_per_step * world * args.steps / float(t[0].item())
+    wp_ms = 1e3 * float(t[1].item()) / args.steps
+    h2d_per_step = st_e2e["h2d_bytes"] / args.steps
+    # informational: the unstaged route (pcf_push_frame uploads the float4 clouds as they are: 16 B/point over PCIe)
+    e2e_raw = None
     if world == 1:
-        host3 = torch.from_numpy(np.ascontiguousarray(frames[:, :, :3])).pin_memory()
-        def ingest_host3():
+        def ingest_raw():
             for i in range(N_FRAMES):
-                fus.push_frame(host3[i], poses[i], first + i)
+                fus.push_frame(host_list[i], poses[i], first + i)
             return fus.count_kept()
-        ingest_host3(); process_and_clear()
+        ingest_raw(); process_and_clear()
         torch.cuda.synchronize()
+        nrep = min(args.steps, 3)
         t0 = time.perf_counter()
-        for s in range(args.steps):
-            ingest_host3()
-            if s + 1 < args.steps:
-                fus.clear()
-        e2e_packed = {"value": points_per_step * args.steps / (time.perf_counter() - t0), "unit": "points/s",
-                      "h2d_bytes_per_step": int(points_per_step * 12), "note": "packed xyz host clouds (stride 3); clear() between steps inside the timed region"}
-        process_and_clear()
-        del host3
+        for s in range(nrep):
+            ingest_raw()
+            fus.clear()
+        e2e_raw = {"value": points_per_step * nrep / (time.perf_counter() - t0), "unit": "points/s",
+                   "h2d_bytes_per_step": int(points_per_step * 16),
+                   "note": "pcf_push_frame: float4 clouds uploaded unstaged; clear() between steps inside the timed region"}
     clocks = sampler.stop()
+    pcie_peak = pinned_copy_peak(local)
+    e2e_step_s = float(t[0].item()) / args.steps
+    e2e_roofline = {"bound": "pcie+host", "achieved": h2d_per_step / e2e_step_s / 1e9, "peak": pcie_peak, "unit": "GB/s",
+                    "frac": h2d_per_step / e2e_step_s / 1e9 / pcie_peak,
+                    "peak_source": "measured in this run: best of 4 x 256 MB pinned H2D copies",
+                    "host_bytes_read_gbs": points_per_step * 16 / e2e_step_s / 1e9,
+                    "bytes_per_input_point_over_pcie": h2d_per_step / points_per_step,
+                    "stage_threads": stage_threads, "host_cpus": n_cpus,
+                    "note": "per rank; the staging threads read every 16-byte input point once and upload only the points inside the depth clip as 12-byte xyz"}
 
     # ---- roofline of the dominant kernel (k_ingest) -----------------------------------------------------------
     launches_per_step = (N_FRAMES + BATCH - 1) // BATCH
@@ -335,6 +536,14 @@ def run_b200(args):
                 "algorithmic_bytes_per_launch": alg_bytes_step / launches_per_step, "launch_ms": per_launch_ms,
                 "kept_fraction": kept / points_per_step}
 
+    fus.close()
+    del dev_frames, host_frames, host_list
+    torch.cuda.empty_cache()
+
+    c3 = None
+    if not args.no_c3:
+        c3 = c3_strong(pcf, sh, local, rank, world, lambda f: sh.PeerExchange(f))
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline_run(frames, poses, grid)
@@ -342,6 +551,7 @@ def run_b200(args):
     if rank == 0:
         line = {
             "metric": "fused points/sec", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+            "value_kind": "hbm_resident_batch (clouds already in HBM, one 200-frame launch; the end-to-end number is e2e)",
             "warmup": args.warmup, "ms_per_step": max_ingest_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64 transform / f32 statistics", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_gpu": N_FRAMES, "points_per_frame": npf, "batch_frames_per_launch": BATCH,
@@ -349,21 +559,25 @@ def run_b200(args):
                        "sharding": f"frames x{world}"},
             "process_ms": statistics.mean(p["update_ms"] + p["extract_device_ms"] + p["extract_d2h_ms"] for p in proc),
             "process_detail": dict({k: statistics.mean(p[k] for p in proc) for k in ("update_ms", "extract_device_ms", "extract_d2h_ms", "voxels")},
-                                   note=("update_ms = exchange (plane histogram + viewpoint all-reduce, count all-gather, ONE compaction+peer-store "
-                                         "kernel over NVLink, barrier); extract_device_ms = install + slab update + extract incl. D2H; "
-                                         "rank 0's view") if world > 1 else "single GPU"),
+                                   note=("update_ms = exchange; extract_device_ms = install + slab update + extract incl. D2H; rank 0's view")
+                                   if world > 1 else "single GPU"),
             "step_wall_ms": 1e3 * t_wall / args.steps,
-            "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(points_per_step * 16),
-                    "d2h_bytes_per_step": 4, "process_wall_ms": statistics.mean(e2e_proc)},
-            "e2e_packed_xyz": e2e_packed,
+            "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(h2d_per_step),
+                    "d2h_bytes_per_step": 4, "route": "pcf_submit_frame (host clip-and-pack staging, node.cpp:218-263) -> H2D -> k_ingest_bulk<12>",
+                    "host_input_bytes_per_step": int(points_per_step * 16)},
+            "e2e_roofline": e2e_roofline,
+            "e2e_raw_float4": e2e_raw,
+            "whole_path": {"ms": wp_ms, "points_per_s": points_per_step * world / (wp_ms * 1e-3),
+                           "what": "200-frame ingest from host clouds (e2e route) + process() (update + extract + result D2H) + clear, wall clock, max over ranks"},
             "ingest_ms_per_rank": [x / args.steps for x in per_rank_ms],
             "gpu_launches": int(st["kernel_launches"]),
             "clocks": clocks, "roofline": roofline, "gen_s": t_gen,
+            "multi_gpu_parity": parity, "multi_gpu_parity_detail": parity_detail,
+            "c3_strong": c3,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
-    fus.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -375,6 +589,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-c3", action="store_true", help="skip the C3 strong-scaling leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

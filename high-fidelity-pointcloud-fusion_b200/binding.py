@@ -25,7 +25,7 @@ class _Config(C.Structure):
     _fields_ = [("box", C.c_double * 6), ("res", C.c_float * 3), ("clip_zmin", C.c_double), ("clip_zmax", C.c_double),
                 ("k_neighbourhood", C.c_int32), ("walk_k", C.c_int32), ("min_neighbours", C.c_int32),
                 ("cylinder_radius", C.c_double), ("ball_radius", C.c_double), ("device", C.c_int32),
-                ("max_frames", C.c_uint32), ("log_capacity_hint", C.c_uint64)]
+                ("max_frames", C.c_uint32), ("log_capacity_hint", C.c_uint64), ("stage_threads", C.c_int32)]
 
 
 class _Result(C.Structure):
@@ -41,12 +41,12 @@ class _State(C.Structure):
 class _Stats(C.Structure):
     _fields_ = [("frames_pushed", C.c_uint64), ("points_offered", C.c_uint64), ("points_kept", C.c_uint64),
                 ("occupied_voxels", C.c_uint64), ("normals_found", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("update_passes", C.c_uint32)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("update_passes", C.c_uint32), ("staged_dropped", C.c_uint64)]
 
 
 ABI_SYMBOLS = [
     "pcf_default_config", "pcf_create", "pcf_destroy", "pcf_last_error", "pcf_dims", "pcf_start", "pcf_stop", "pcf_reset",
-    "pcf_push_frame", "pcf_push_pointcloud2", "pcf_add_points", "pcf_host_alloc", "pcf_host_free", "pcf_upload_ticket", "pcf_wait_upload", "pcf_push_frames_device", "pcf_sync", "pcf_count_kept", "pcf_update", "pcf_extract", "pcf_process", "pcf_write_result",
+    "pcf_push_frame", "pcf_push_pointcloud2", "pcf_add_points", "pcf_submit_frame", "pcf_submit_pointcloud2", "pcf_drain", "pcf_stage_frame", "pcf_staged_count", "pcf_wait_staged", "pcf_host_alloc", "pcf_host_free", "pcf_upload_ticket", "pcf_wait_upload", "pcf_push_frames_device", "pcf_sync", "pcf_count_kept", "pcf_update", "pcf_extract", "pcf_process", "pcf_write_result",
     "pcf_extract_hq", "pcf_clear", "pcf_dump_state", "pcf_get_stats", "pcf_reset_stats", "pcf_last_timings", "pcf_stream",
     "pcf_grid_buffer", "pcf_viewpoint_table", "pcf_log_compact", "pcf_log_replace", "pcf_set_slab", "pcf_plane_counts", "pcf_plane_point_counts", "pcf_exchange_counts", "pcf_exchange_scatter", "pcf_recv_buffer", "pcf_ipc_export", "pcf_ipc_open",
     "pcf_ipc_close_all", "pcf_install_records", "pcf_get_viewpoints", "pcf_set_viewpoints", "pcf_enable_peer_access", "pcf_kat_transform_voxel",
@@ -74,11 +74,16 @@ def load_library():
     lib.pcf_last_error.argtypes = [vp]
     lib.pcf_last_error.restype = C.c_char_p
     lib.pcf_dims.argtypes = [vp, C.POINTER(C.c_int32 * 3)]
-    for name in ["pcf_start", "pcf_stop", "pcf_reset", "pcf_sync", "pcf_update", "pcf_clear", "pcf_reset_stats"]:
+    for name in ["pcf_start", "pcf_stop", "pcf_reset", "pcf_sync", "pcf_update", "pcf_clear", "pcf_reset_stats", "pcf_drain"]:
         getattr(lib, name).argtypes = [vp]
     lib.pcf_push_frame.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32]
     lib.pcf_push_pointcloud2.argtypes = [vp, vp] + [C.c_uint32] * 7 + [vp, C.c_uint32]
     lib.pcf_add_points.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32]
+    lib.pcf_submit_frame.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32]
+    lib.pcf_submit_pointcloud2.argtypes = [vp, vp] + [C.c_uint32] * 7 + [vp, C.c_uint32]
+    lib.pcf_stage_frame.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, C.POINTER(C.c_uint32)]
+    lib.pcf_staged_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+    lib.pcf_wait_staged.argtypes = [vp, C.c_uint64]
     lib.pcf_host_alloc.argtypes = [C.c_size_t]
     lib.pcf_host_alloc.restype = vp
     lib.pcf_host_free.argtypes = [vp]
@@ -173,7 +178,7 @@ class Fusion:
     """One fusion context on one GPU (= the reference's PointcloudFusion + OccupancyGrid pair)."""
 
     def __init__(self, box, res, clip_zmin=0.28, clip_zmax=0.6, device=0, max_frames=1 << 16, log_capacity_hint=0,
-                 walk_k=3, min_neighbours=20, started=True):
+                 walk_k=3, min_neighbours=20, started=True, stage_threads=0):
         self.lib = load_library()
         cfg = _Config()
         self.lib.pcf_default_config(C.byref(cfg))
@@ -183,6 +188,7 @@ class Fusion:
         cfg.clip_zmin, cfg.clip_zmax = clip_zmin, clip_zmax
         cfg.device, cfg.max_frames, cfg.log_capacity_hint = device, max_frames, log_capacity_hint
         cfg.walk_k, cfg.min_neighbours = walk_k, min_neighbours
+        cfg.stage_threads = stage_threads
         h = C.c_void_p()
         rc = self.lib.pcf_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -231,6 +237,29 @@ class Fusion:
         pose = np.ascontiguousarray(pose, np.float64).reshape(16)
         return self._ck(self.lib.pcf_push_pointcloud2(self.h, _ptr(data), width, height, point_step, row_step, offsets[0], offsets[1],
                                                       offsets[2], pose.ctypes.data, frame_idx))
+
+    def submit_frame(self, pts, pose, frame_idx):
+        """Asynchronous push through the host staging pool (clip-and-pack, node.cpp:218-263): `pts` (host memory, pageable or
+        pinned) and `pose` (float64[16], C-contiguous) must stay alive until drain() / sync() / count_kept() / update()."""
+        n, stride = pts.shape
+        return self._ck(self.lib.pcf_submit_frame(self.h, _ptr(pts), n, stride, _ptr(pose), frame_idx))
+
+    def submit_pointcloud2(self, data, width, height, point_step, row_step, offsets, pose, frame_idx):
+        pose = np.ascontiguousarray(pose, np.float64).reshape(16)
+        return self._ck(self.lib.pcf_submit_pointcloud2(self.h, _ptr(data), width, height, point_step, row_step, offsets[0], offsets[1],
+                                                        offsets[2], pose.ctypes.data, frame_idx))
+
+    def drain(self):
+        self._ck(self.lib.pcf_drain(self.h))
+
+    def stage_frame(self, pts, out=None):
+        """pcf_stage_frame: clip-and-pack on the calling thread.  Returns (staged float32 [m, 3], m)."""
+        n, stride = pts.shape
+        if out is None:
+            out = np.empty((n + 4, 3), np.float32)
+        m = C.c_uint32()
+        self._ck(self.lib.pcf_stage_frame(self.h, _ptr(pts), n, stride, _ptr(out), C.byref(m)))
+        return out[:m.value], int(m.value)
 
     def add_points(self, pts_world, viewpoint, frame_idx):
         """OccupancyGrid::addPoints (OG.hpp:185): cloud already in the fusion frame + explicit viewpoint."""

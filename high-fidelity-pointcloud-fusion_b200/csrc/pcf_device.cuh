@@ -248,10 +248,16 @@ struct Stats {     // the scored part of VoxelInfo (OG.hpp:64-68,73); mean_dist 
 PCF_HD void stats_init(Stats& s) {
     s.centroid = mk(0, 0, 0); s.sd = mk(0, 0, 0); s.sd_dist = 0.f; s.mean_dist = 0.f; s.count = 0;
 }
-PCF_HD void score_point(const GridParams& g, const Axis& ax, Stats& s, V3 pt) {
-    V3 proj = project(ax, pt);
+// The cylinder test of one point is independent of every other point; only the fold of the in-cylinder points into
+// the running statistics is an ordered recurrence.  score_test / score_fold split the two so that the scoring kernel
+// can evaluate several tests back to back (independent instruction chains) before folding them in buffer order.
+PCF_HD float score_test(const Axis& ax, V3 pt, V3& proj) {
+    proj = project(ax, pt);
     V3 diff = pt - proj;
-    double dist = (double)sqrtf(sqnorm(diff));
+    return sqrtf(sqnorm(diff));
+}
+PCF_HD void score_fold(const GridParams& g, Stats& s, V3 proj, float dist_f) {
+    double dist = (double)dist_f;
     if (dist < g.cylinder_radius) {
         s.count++;
         V3 old_mean = s.centroid;
@@ -266,6 +272,11 @@ PCF_HD void score_point(const GridParams& g, const Axis& ax, Stats& s, V3 pt) {
         s.sd_dist = (float)((double)s.sd_dist +
                             ((dist - (double)s.mean_dist) * (dist - (double)old_md) - (double)s.sd_dist) / dc);
     }
+}
+PCF_HD void score_point(const GridParams& g, const Axis& ax, Stats& s, V3 pt) {
+    V3 proj;
+    float d = score_test(ax, pt, proj);
+    score_fold(g, s, proj, d);
 }
 
 // ---- PCA normal ---------------------------------------------------------------------------------------------

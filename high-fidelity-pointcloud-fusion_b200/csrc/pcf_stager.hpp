@@ -1,0 +1,180 @@
+// pcf_stager.hpp -- host staging pool of libpcfusion.so (plain C++17, no CUDA types on this side).
+//
+// Replaces the reference's first pipeline stage: the `addPoints()` thread that pops a PointCloud2 message from `clouds_`,
+// decodes it and copies the points inside the camera-frame depth clip into `clouds_processed_` (node.cpp:218-263,
+// decode node.cpp:182-216, clip node.cpp:248-255).  Here a pool of threads does that walk once per message, in
+// parallel ACROSS frames: every point is read, points outside the clip are dropped (the float thresholds are the
+// ones the kernel uses, exactly equivalent to the reference's double compares), and the survivors are packed, in
+// point order, as 12-byte xyz into a pinned slot.  Slots are handed to the GPU strictly in submission order, so the
+// arrival order every per-voxel buffer depends on (OG.hpp:211,230,239) is unchanged; the kernel still applies the
+// FP64 transform, the box test and (again, harmlessly) the clip.  What crosses PCIe is the clipped cloud
+// (C2: 5.5 instead of 16 bytes per input point), which is what bounds the end-to-end rate.
+#pragma once
+#include <condition_variable>
+#include <cstdint>
+#include <cstring>
+#include <deque>
+#include <functional>
+#include <limits>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace pcf {
+
+struct StageJob {
+    const uint8_t* data = nullptr;   // first byte of the cloud (message payload); must stay valid until the job is staged
+    uint32_t rows = 1, cols = 0;     // organized cloud: rows x cols points (flat cloud: 1 x n)
+    uint64_t row_step = 0;           // bytes between rows
+    uint32_t point_step = 16;        // bytes between points of a row
+    uint32_t x_offset = 0;           // byte offset of the float32 x field; y and z follow it
+    double pose[16];
+    uint32_t frame_idx = 0;
+};
+
+// Order-preserving clip-and-pack of one cloud.  `out` must hold 3 * (rows * cols + 4) floats.  Returns the number of
+// packed points, padded with NaN points (which fail the kernel's clip) to a multiple of 4 so that every 256-point
+// chunk of the packed cloud is a 16-byte multiple for the bulk-copy kernel.
+inline uint32_t clip_pack(const StageJob& j, float clip_lo, float clip_hi, float* out) {
+    uint32_t k = 0;
+    for (uint32_t r = 0; r < j.rows; r++) {
+        const uint8_t* p = j.data + (size_t)r * j.row_step + j.x_offset;
+        const uint32_t step = j.point_step;
+        for (uint32_t c = 0; c < j.cols; c++, p += step) {
+            float v[3];
+            std::memcpy(v, p, 12);
+            out[3 * (size_t)k] = v[0];
+            out[3 * (size_t)k + 1] = v[1];
+            out[3 * (size_t)k + 2] = v[2];
+            k += (v[2] > clip_lo && v[2] < clip_hi) ? 1u : 0u;       // node.cpp:251; NaN fails
+        }
+    }
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    while (k & 3u) { out[3 * (size_t)k] = 0.f; out[3 * (size_t)k + 1] = 0.f; out[3 * (size_t)k + 2] = nan; k++; }
+    return k;
+}
+
+class Stager {
+   public:
+    struct Hooks {
+        std::function<void*(size_t)> alloc_pinned;
+        std::function<void(void*)> free_pinned;
+        std::function<void(int)> thread_init;                       // once per worker thread (cudaSetDevice)
+        std::function<void(int)> slot_wait;                         // block until the last upload out of slot s has completed
+        // hand a staged cloud to the GPU (H2D copy + integration launch); called in submission order, one at a time
+        std::function<int(int slot, const float* xyz, uint32_t n_staged, uint32_t n_offered, const double* pose, uint32_t frame_idx)> push;
+    };
+
+    Stager(int threads, float clip_lo, float clip_hi, Hooks hooks)
+        : clip_lo_(clip_lo), clip_hi_(clip_hi), hooks_(std::move(hooks)) {
+        n_threads_ = threads < 1 ? 1 : threads;
+        slots_.resize((size_t)n_threads_ * 2);
+        max_queue_ = (size_t)n_threads_ * 4;
+        for (int t = 0; t < n_threads_; t++) pool_.emplace_back(&Stager::worker, this);
+    }
+    ~Stager() {
+        drain();
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            quit_ = true;
+        }
+        cv_work_.notify_all();
+        cv_order_.notify_all();
+        for (std::thread& t : pool_) t.join();
+        for (Slot& s : slots_) if (s.p) hooks_.free_pinned(s.p);
+    }
+    int n_slots() const { return (int)slots_.size(); }
+    int n_threads() const { return n_threads_; }
+
+    void submit(const StageJob& j) {                                 // node.cpp:345-347 (clouds_.push_back)
+        std::unique_lock<std::mutex> lk(m_);
+        cv_space_.wait(lk, [&] { return queue_.size() < max_queue_; });
+        queue_.push_back(j);
+        lk.unlock();
+        cv_work_.notify_one();
+    }
+    // node.cpp:356: drop what no worker has taken yet.  Returns the number of dropped clouds.
+    size_t drop_queued() {
+        std::lock_guard<std::mutex> lk(m_);
+        size_t n = queue_.size();
+        queue_.clear();
+        cv_space_.notify_all();
+        cv_order_.notify_all();
+        return n;
+    }
+    // wait until every submitted cloud has been handed to the GPU; returns the first push error (0 = none) and clears it
+    int drain() {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_order_.wait(lk, [&] { return queue_.empty() && next_push_ == next_seq_; });
+        int rc = err_;
+        err_ = 0;
+        return rc;
+    }
+    // number of clouds handed to the GPU so far (their source buffers are no longer read)
+    uint64_t staged() {
+        std::lock_guard<std::mutex> lk(m_);
+        return next_push_;
+    }
+    // block until `n` clouds have been handed over -- or nothing is pending any more (the n-th may have been dropped)
+    void wait_staged(uint64_t n) {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_order_.wait(lk, [&] { return next_push_ >= n || (queue_.empty() && next_push_ == next_seq_); });
+    }
+
+   private:
+    struct Slot { float* p = nullptr; size_t cap = 0; };
+
+    void worker() {
+        if (hooks_.thread_init) hooks_.thread_init(0);
+        for (;;) {
+            StageJob j;
+            uint64_t seq;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_work_.wait(lk, [&] { return quit_ || !queue_.empty(); });
+                if (queue_.empty()) return;                          // quit
+                j = queue_.front();
+                queue_.pop_front();
+                seq = next_seq_++;                                   // taken in FIFO order under the lock: seq order == submission order
+                cv_space_.notify_one();
+                // the slot was last used by cloud seq - n_slots: that one must have been handed over before it is refilled
+                const uint64_t ns = slots_.size();
+                cv_order_.wait(lk, [&] { return seq < ns || next_push_ > seq - ns; });
+            }
+            const int s = (int)(seq % slots_.size());
+            hooks_.slot_wait(s);
+            Slot& sl = slots_[s];
+            const size_t need = 3 * ((size_t)j.rows * j.cols + 4);
+            if (need > sl.cap) {
+                if (sl.p) hooks_.free_pinned(sl.p);
+                sl.cap = need + need / 8;
+                sl.p = static_cast<float*>(hooks_.alloc_pinned(sl.cap * sizeof(float)));
+            }
+            uint32_t n = 0;
+            if (sl.p) n = clip_pack(j, clip_lo_, clip_hi_, sl.p);
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_order_.wait(lk, [&] { return next_push_ == seq; });
+                int rc = sl.p ? hooks_.push(s, sl.p, n, j.rows * j.cols, j.pose, j.frame_idx) : -2;
+                if (rc < 0 && err_ == 0) err_ = rc;
+                next_push_++;
+            }
+            cv_order_.notify_all();
+        }
+    }
+
+    float clip_lo_, clip_hi_;
+    Hooks hooks_;
+    int n_threads_ = 1;
+    std::vector<Slot> slots_;
+    std::vector<std::thread> pool_;
+    std::deque<StageJob> queue_;
+    size_t max_queue_ = 8;
+    std::mutex m_;
+    std::condition_variable cv_work_, cv_space_, cv_order_;
+    uint64_t next_seq_ = 0, next_push_ = 0;
+    int err_ = 0;
+    bool quit_ = false;
+};
+
+}  // namespace pcf

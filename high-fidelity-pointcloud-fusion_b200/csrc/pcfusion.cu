@@ -10,11 +10,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pcfusion.h"
 #include "pcf_kernels.cuh"
+#include "pcf_stager.hpp"
 
 using namespace pcf;
 
@@ -52,7 +55,9 @@ struct pcf_ctx {
     uint32_t* occ_bits = nullptr;
     uint32_t* occ_rank = nullptr;
     uint64_t n_words = 0;
-    bool occ_dirty = true;
+    bool occ_dirty = true;                // occ_rank / n_vox are stale (the bitmap itself is kept current by the ingest kernels)
+    bool occ_from_grid = false;           // a caller reduced the dense grid externally (pcf_grid_buffer): rebuild the bitmap from it
+    bool log_installed = false;           // the log came from pcf_install_records / pcf_log_replace: chunk_frame no longer describes it
     uint32_t n_vox = 0;                   // occupied cells at the last bitmap build
     float4* vp_table = nullptr;
     // point log
@@ -82,10 +87,16 @@ struct pcf_ctx {
     int ring_pos = 0;
     cudaEvent_t ev_upload[kTickets] = {};
     uint64_t uploads = 0;                 // ticket of the most recent host push
+    // host staging pool (pcf_submit_*): clip-and-pack threads + pinned slots, see pcf_stager.hpp
+    std::unique_ptr<pcf::Stager> stager;
+    std::vector<cudaEvent_t> slot_ev;     // per pinned slot: its last upload has left the slot
+    uint64_t staged_dropped = 0;          // clouds dropped by pcf_reset before a staging thread took them
 
     // scratch
     DevBuf scan1, scan2, tmpA, tmpB, tmpC, tmpD, hist, sort_tab, keysA, keysB, valsA, valsB, sorted, uv_cell, uv_off, nidx,
-        sc_a, sc_b, sc_c, flags, slots, cand, res_dev, total_dev;
+        sc_a, sc_b, sc_c, flags, slots, cand, res_dev, total_dev, sc_keys, sc_ids, sc_order, sc_okeys, sc_tab;
+    int score_unroll = 2;                 // PCF_SCORE_UNR: cylinder tests evaluated back to back in k_score (1, 2 or 4)
+    bool score_balance = true;            // PCF_SCORE_BALANCE=0 keeps the x-major voxel -> lane assignment
     uint32_t* total_host = nullptr;       // pinned, 4 words
     // host results (pinned)
     void* res_host = nullptr;
@@ -215,6 +226,8 @@ int build_grid_params(pcf_ctx* c) {
 }
 
 // ---- device-wide exclusive scan (in == out allowed); optional total to total_dev[slot] --------------------
+// POPC: the input words are bitmaps and their population counts are scanned (occupancy bitmap -> rank)
+template <bool POPC = false>
 int scan_u32(pcf_ctx* c, const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* total_dev) {
     if (n == 0) {
         if (total_dev) CU(cudaMemsetAsync(total_dev, 0, 4, c->stream));
@@ -222,25 +235,25 @@ int scan_u32(pcf_ctx* c, const uint32_t* in, uint32_t* out, uint64_t n, uint32_t
     }
     uint32_t nb1 = div_up(n, kChunk);
     if (nb1 == 1) {
-        LAUNCH(c, k_scan_tiles, 1, kBlock, in, out, n, (const uint32_t*)nullptr, total_dev);
+        LAUNCH(c, k_scan_tiles<POPC>, 1, kBlock, in, out, n, (const uint32_t*)nullptr, total_dev);
         return PCF_OK;
     }
     int rc = reserve(c, c->scan1, (size_t)nb1 * 4);
     if (rc) return rc;
     uint32_t* s1 = (uint32_t*)c->scan1.p;
-    LAUNCH(c, k_block_sums, nb1, kBlock, in, n, s1);
+    LAUNCH(c, k_block_sums<POPC>, nb1, kBlock, in, n, s1);
     uint32_t nb2 = div_up(nb1, kChunk);
     if (nb2 == 1) {
-        LAUNCH(c, k_scan_tiles, 1, kBlock, s1, s1, (uint64_t)nb1, (const uint32_t*)nullptr, (uint32_t*)nullptr);
+        LAUNCH(c, k_scan_tiles<false>, 1, kBlock, s1, s1, (uint64_t)nb1, (const uint32_t*)nullptr, (uint32_t*)nullptr);
     } else {
         rc = reserve(c, c->scan2, (size_t)nb2 * 4);
         if (rc) return rc;
         uint32_t* s2 = (uint32_t*)c->scan2.p;
-        LAUNCH(c, k_block_sums, nb2, kBlock, s1, (uint64_t)nb1, s2);
-        LAUNCH(c, k_scan_tiles, 1, kBlock, s2, s2, (uint64_t)nb2, (const uint32_t*)nullptr, (uint32_t*)nullptr);   // nb2 <= 2048
-        LAUNCH(c, k_scan_tiles, nb2, kBlock, s1, s1, (uint64_t)nb1, s2, (uint32_t*)nullptr);
+        LAUNCH(c, k_block_sums<false>, nb2, kBlock, s1, (uint64_t)nb1, s2);
+        LAUNCH(c, k_scan_tiles<false>, 1, kBlock, s2, s2, (uint64_t)nb2, (const uint32_t*)nullptr, (uint32_t*)nullptr);   // nb2 <= 2048
+        LAUNCH(c, k_scan_tiles<false>, nb2, kBlock, s1, s1, (uint64_t)nb1, s2, (uint32_t*)nullptr);
     }
-    LAUNCH(c, k_scan_tiles, nb1, kBlock, in, out, n, s1, total_dev);
+    LAUNCH(c, k_scan_tiles<POPC>, nb1, kBlock, in, out, n, s1, total_dev);
     return PCF_OK;
 }
 
@@ -277,15 +290,16 @@ int ensure_log(pcf_ctx* c, uint32_t need_chunks) {
     return PCF_OK;
 }
 
-// occupancy bitmap + rank from the dense grid (shared by update and extraction)
+// occupancy rank (cell -> compact voxel id) from the bitmap (shared by update and extraction).  The bitmap is maintained
+// by the ingest kernels, so this reads cells/8 bytes twice instead of sweeping the 4-byte-per-cell grid.
 int build_occupancy(pcf_ctx* c) {
     if (!c->occ_dirty) return PCF_OK;
-    int rc = reserve(c, c->tmpA, (size_t)c->n_words * 4);
-    if (rc) return rc;
-    uint32_t* pop = (uint32_t*)c->tmpA.p;
-    LAUNCH(c, k_cells_to_bits, div_up(c->n_words, kBlock), kBlock, c->first_frame, c->g, c->occ_bits, pop, c->n_words);
+    if (c->occ_from_grid) {
+        LAUNCH(c, k_cells_to_bits, div_up(c->n_words, kBlock), kBlock, c->first_frame, c->g, c->occ_bits, c->n_words);
+        c->occ_from_grid = false;
+    }
     uint32_t* tot = (uint32_t*)c->total_dev.p;
-    rc = scan_u32(c, pop, c->occ_rank, c->n_words, tot);
+    int rc = scan_u32<true>(c, c->occ_bits, c->occ_rank, c->n_words, tot);
     if (rc) return rc;
     rc = read_total(c, tot, &c->n_vox);
     if (rc) return rc;
@@ -315,9 +329,10 @@ int flush_holders(pcf_ctx* c) {
 
 // one launch over `nf` equally sized clouds resident in device memory.  Batch = IngestBatch (up to 256 frames, 24 KB of
 // kernel parameters) or IngestBatch1 (one frame, 144 bytes: the per-frame host path launches 200 times per step).
+// stride: floats per point; 0 = organized PointCloud2 layout described by `rows` (generic kernel only)
 template <class Batch>
 int launch_ingest_t(pcf_ctx* c, const float* pts_dev, uint64_t frame_stride, uint32_t n, uint32_t nf, uint32_t stride,
-                    const double* poses, uint32_t first_frame_idx, const float* explicit_vp) {
+                    const double* poses, uint32_t first_frame_idx, const float* explicit_vp, const RowLayout* rows) {
     static thread_local Batch b;
     const GridParams& g = c->g;
     uint32_t chunks = div_up(n, kWChunk);
@@ -333,9 +348,11 @@ int launch_ingest_t(pcf_ctx* c, const float* pts_dev, uint64_t frame_stride, uin
     b.vp[3] = 1.f;
     for (uint32_t f = 0; f < nf; f++)
         for (int i = 0; i < 12; i++) b.T[f][i] = poses[(size_t)f * 16 + i];
+    RowLayout rl{n ? n : 1u, stride, 0};
+    if (rows) rl = *rows;
     if (explicit_vp) {       // pcf_add_points: cloud already in the fusion frame
         dim3 grid(div_up(chunks, kWarps), nf, 1);
-        LAUNCH(c, (k_ingest<0, true, Batch>), grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
+        LAUNCH(c, (k_ingest<0, true, Batch>), grid, kBlock, b, rl, g, c->first_frame, c->occ_bits, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
         CU(cudaGetLastError());
         c->n_chunks += chunks * nf;
         return PCF_OK;
@@ -344,24 +361,24 @@ int launch_ingest_t(pcf_ctx* c, const float* pts_dev, uint64_t frame_stride, uin
     const bool aligned = ((uintptr_t)pts_dev % 16 == 0) && ((frame_stride * 4) % 16 == 0 || nf == 1);
     const uint32_t total = chunks * nf;
     const uint32_t grid_bulk = std::min<uint32_t>((uint32_t)(c->sm_count * c->ctas_per_sm), div_up(total, kWarps));
-    if (c->use_bulk && aligned && stride == 4) {
-        LAUNCH_SMEM(c, (k_ingest_bulk<16, kBulkMinBlocks, kBulkRounds, 1, Batch>), grid_bulk, kBlock, kWarps * kWChunk * 16, b, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
-    } else if (c->use_bulk && aligned && stride == 3 && n % 4 == 0) {
-        LAUNCH_SMEM(c, (k_ingest_bulk<12, kBulkMinBlocks, kBulkRounds, 1, Batch>), grid_bulk, kBlock, kWarps * kWChunk * 12, b, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
+    if (c->use_bulk && aligned && stride == 4 && !rows) {
+        LAUNCH_SMEM(c, (k_ingest_bulk<16, kBulkMinBlocks, kBulkRounds, 1, Batch>), grid_bulk, kBlock, kWarps * kWChunk * 16, b, g, c->first_frame, c->occ_bits, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
+    } else if (c->use_bulk && aligned && stride == 3 && n % 4 == 0 && !rows) {
+        LAUNCH_SMEM(c, (k_ingest_bulk<12, kBulkMinBlocks, kBulkRounds, 1, Batch>), grid_bulk, kBlock, kWarps * kWChunk * 12, b, g, c->first_frame, c->occ_bits, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
     } else {
         dim3 grid(div_up(chunks, kWarps), nf, 1);
-        if (stride == 4) LAUNCH(c, (k_ingest<4, false, Batch>), grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
-        else if (stride == 3) LAUNCH(c, (k_ingest<3, false, Batch>), grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
-        else LAUNCH(c, (k_ingest<0, false, Batch>), grid, kBlock, b, stride, g, c->first_frame, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
+        if (stride == 4 && !rows) LAUNCH(c, (k_ingest<4, false, Batch>), grid, kBlock, b, rl, g, c->first_frame, c->occ_bits, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
+        else if (stride == 3 && !rows) LAUNCH(c, (k_ingest<3, false, Batch>), grid, kBlock, b, rl, g, c->first_frame, c->occ_bits, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
+        else LAUNCH(c, (k_ingest<0, false, Batch>), grid, kBlock, b, rl, g, c->first_frame, c->occ_bits, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
     }
     CU(cudaGetLastError());
     c->n_chunks += chunks * nf;
     return PCF_OK;
 }
 int launch_ingest(pcf_ctx* c, const float* pts_dev, uint64_t frame_stride, uint32_t n, uint32_t nf, uint32_t stride,
-                  const double* poses, uint32_t first_frame_idx, const float* explicit_vp = nullptr) {
-    if (nf == 1) return launch_ingest_t<IngestBatch1>(c, pts_dev, frame_stride, n, nf, stride, poses, first_frame_idx, explicit_vp);
-    return launch_ingest_t<IngestBatch>(c, pts_dev, frame_stride, n, nf, stride, poses, first_frame_idx, explicit_vp);
+                  const double* poses, uint32_t first_frame_idx, const float* explicit_vp = nullptr, const RowLayout* rows = nullptr) {
+    if (nf == 1) return launch_ingest_t<IngestBatch1>(c, pts_dev, frame_stride, n, nf, stride, poses, first_frame_idx, explicit_vp, rows);
+    return launch_ingest_t<IngestBatch>(c, pts_dev, frame_stride, n, nf, stride, poses, first_frame_idx, explicit_vp, rows);
 }
 
 int check_frame_idx(pcf_ctx* c, uint32_t first, uint32_t count) {
@@ -472,14 +489,39 @@ int run_scoring(pcf_ctx* c) {
     ScoreOut so{(float4*)c->sc_a.p, (float4*)c->sc_b.p, (float*)c->sc_c.p};
     uint32_t* fault = (uint32_t*)c->total_dev.p + 8;
     CU(cudaMemsetAsync(fault, 0, 32, c->stream));
+    // work-balanced voxel -> lane assignment: stable one-pass counting sort of the voxel ids by an 8-bit work key
+    const uint32_t* order = nullptr;
+    if (c->score_balance && nn > 4096) {
+        const uint32_t nt = div_up(nn, kChunk);
+        if ((rc = reserve(c, c->sc_keys, (size_t)nn * 4))) return rc;
+        if ((rc = reserve(c, c->sc_ids, (size_t)nn * 4))) return rc;
+        if ((rc = reserve(c, c->sc_okeys, (size_t)nn * 4))) return rc;
+        if ((rc = reserve(c, c->sc_order, (size_t)nn * 4))) return rc;
+        if ((rc = reserve(c, c->hist, (size_t)256 * nt * 4))) return rc;
+        if ((rc = reserve(c, c->sc_tab, (size_t)nt * sizeof(SortTile) + 16))) return rc;
+        SortTile* tab = (SortTile*)c->sc_tab.p;
+        uint32_t* nt_dev = (uint32_t*)(tab + nt);
+        LAUNCH(c, k_score_work, div_up(nn, kBlock), kBlock, (const uint32_t*)c->n_cell.p, (const float4*)c->n_nrm.p, nn, c->g, c->occ_bits,
+               c->occ_rank, (const uint32_t*)c->uv_off.p, (uint32_t*)c->sc_keys.p, (uint32_t*)c->sc_ids.p);
+        LAUNCH(c, k_sort_flat_tiles, div_up(nt, kBlock), kBlock, nn, tab, nt_dev);
+        SortSrc src{};
+        src.keys = (const uint32_t*)c->sc_keys.p; src.vals = (const uint32_t*)c->sc_ids.p; src.tab = tab; src.n_tiles_dev = nt_dev;
+        uint32_t* hist = (uint32_t*)c->hist.p;
+        LAUNCH(c, k_sort_hist<false>, nt, kBlock, src, 0u, 255u, hist);
+        if ((rc = scan_u32(c, hist, hist, (uint64_t)256 * nt, nullptr))) return rc;
+        LAUNCH(c, k_sort_scatter<false>, nt, kBlock, src, 0u, 255u, hist, (uint32_t*)c->sc_okeys.p, (uint32_t*)c->sc_order.p);
+        order = (const uint32_t*)c->sc_order.p;
+    }
     // canonical schedule: one update pass that saw every point currently in the log
     const bool simple = c->marks.size() == 1 && c->marks[0] == c->n_chunks * (uint32_t)kWChunk && !c->holder;
-    if (simple) LAUNCH(c, k_score<true>, div_up(nn, 128), 128, (const uint32_t*)c->n_cell.p, (const float4*)c->n_nrm.p, (const uint32_t*)c->n_mark.p, nn,
-           c->g, c->occ_bits, c->occ_rank, (const uint32_t*)c->uv_off.p, (const uint32_t*)c->nidx.p, (const float4*)c->sorted.p,
-           (const uint32_t*)c->holder, so, (uint32_t)c->n_points, (const uint32_t*)c->uv_cell.p, fault);
-    else LAUNCH(c, k_score<false>, div_up(nn, 128), 128, (const uint32_t*)c->n_cell.p, (const float4*)c->n_nrm.p, (const uint32_t*)c->n_mark.p, nn,
-           c->g, c->occ_bits, c->occ_rank, (const uint32_t*)c->uv_off.p, (const uint32_t*)c->nidx.p, (const float4*)c->sorted.p,
-           (const uint32_t*)c->holder, so, (uint32_t)c->n_points, (const uint32_t*)c->uv_cell.p, fault);
+#define SCORE_ARGS order, (const uint32_t*)c->n_cell.p, (const float4*)c->n_nrm.p, (const uint32_t*)c->n_mark.p, nn, c->g, c->occ_bits, c->occ_rank, \
+                   (const uint32_t*)c->uv_off.p, (const uint32_t*)c->nidx.p, (const float4*)c->sorted.p, (const uint32_t*)c->holder, so,  \
+                   (uint32_t)c->n_points, (const uint32_t*)c->uv_cell.p, fault
+    if (!simple) LAUNCH(c, (k_score<false, 1>), div_up(nn, 128), 128, SCORE_ARGS);
+    else if (c->score_unroll >= 4) LAUNCH(c, (k_score<true, 4>), div_up(nn, 128), 128, SCORE_ARGS);
+    else if (c->score_unroll >= 2) LAUNCH(c, (k_score<true, 2>), div_up(nn, 128), 128, SCORE_ARGS);
+    else LAUNCH(c, (k_score<true, 1>), div_up(nn, 128), 128, SCORE_ARGS);
+#undef SCORE_ARGS
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->total_host + 8, fault, 32, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -558,11 +600,14 @@ int extract_impl(pcf_ctx* c, int32_t min_count, pcf_result* out) {
 void destroy_impl(pcf_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->stager) { c->stager->drain(); c->stager.reset(); }      // joins the staging threads, frees the pinned slots
+    for (cudaEvent_t e : c->slot_ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     DevBuf* bufs[] = {&c->n_cell, &c->n_nrm, &c->n_mark, &c->scan1, &c->scan2, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->hist, &c->sort_tab,
                       &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->sorted, &c->uv_cell, &c->uv_off, &c->nidx, &c->sc_a, &c->sc_b,
-                      &c->sc_c, &c->flags, &c->slots, &c->cand, &c->res_dev, &c->total_dev, &c->dense_log};
+                      &c->sc_c, &c->flags, &c->slots, &c->cand, &c->res_dev, &c->total_dev, &c->dense_log, &c->sc_keys, &c->sc_ids,
+                      &c->sc_order, &c->sc_okeys, &c->sc_tab};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     void* raw[] = {c->first_frame, c->holder, c->nrm_bits, c->occ_bits, c->occ_rank, c->vp_table, c->log, c->chunk_count, c->chunk_frame, c->recv_buf};
     for (void* p : raw) if (p) cudaFree(p);
@@ -596,12 +641,29 @@ int reset_grid_state(pcf_ctx* c) {
     c->marks.clear();
     c->pending_holder.clear();
     c->occ_dirty = true;
+    c->occ_from_grid = false;
+    c->log_installed = false;
     c->sorted_valid = false;
     c->last_frame_idx = -1;
     c->slab_lo = 0;
     c->slab_hi = -1;
     return PCF_OK;
 }
+
+// Every entry point that touches the grid first lets the staging pool hand over what was submitted before it:
+// submission order == integration order, whatever mix of pcf_submit_* and direct calls the caller uses.
+int drain_staged(pcf_ctx* c) {
+    if (!c->stager) return PCF_OK;
+    int rc = c->stager->drain();
+    if (rc < 0 && c->err.empty()) c->err = "a staged frame failed to integrate";
+    return rc < 0 ? rc : PCF_OK;
+}
+#define ENTER(c)                                  \
+    do {                                          \
+        CU(cudaSetDevice((c)->device));           \
+        int rc_ = drain_staged(c);                \
+        if (rc_) return rc_;                      \
+    } while (0)
 
 }  // namespace
 
@@ -624,6 +686,7 @@ void pcf_default_config(pcf_config* cfg) {
     cfg->device = 0;
     cfg->max_frames = 1u << 16;
     cfg->log_capacity_hint = 0;
+    cfg->stage_threads = 0;                                   // auto
 }
 
 int pcf_create(const pcf_config* cfg, pcf_ctx** out) {
@@ -656,6 +719,10 @@ int pcf_create(const pcf_config* cfg, pcf_ctx** out) {
         c->trace = t && atoi(t) > 0;
         const char* e = getenv("PCF_INGEST");
         c->use_bulk = !(e && strcmp(e, "generic") == 0);
+        const char* u = getenv("PCF_SCORE_UNR");
+        if (u && atoi(u) > 0) c->score_unroll = atoi(u);
+        const char* bl = getenv("PCF_SCORE_BALANCE");
+        if (bl) c->score_balance = atoi(bl) != 0;
     }
     CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -697,28 +764,27 @@ int pcf_dims(const pcf_ctx* ctx, int32_t dims[3]) {
 int pcf_start(pcf_ctx* c) { if (!c) return PCF_ERR_INVALID; c->started = true; return PCF_OK; }
 int pcf_stop(pcf_ctx* c) { if (!c) return PCF_ERR_INVALID; c->started = false; return PCF_OK; }
 int pcf_reset(pcf_ctx* c) {
-    // node.cpp:351-359 clears the not-yet-processed input deque and leaves the grid alone.  Frames handed to
-    // pcf_push_* are already queued on the device, which corresponds to "already popped by the worker thread";
-    // there is no host-side backlog to drop, so reset only has to keep the service contract (grid untouched).
+    // node.cpp:351-359: start_ = false and clouds_.clear() -- the clouds no staging thread has taken yet are dropped,
+    // those already taken (the reference's clouds_processed_ deque) still integrate, the grid is left alone.
     if (!c) return PCF_ERR_INVALID;
+    c->started = false;
+    if (c->stager) c->staged_dropped += c->stager->drop_queued();
     return PCF_OK;
 }
 
-static int push_host_cloud(pcf_ctx* c, const float* pts_host, uint32_t n, uint32_t stride, const double pose[16],
-                           const float* explicit_vp, uint32_t frame_idx) {
-    if (!c) return PCF_ERR_INVALID;
-    if (!c->started) return PCF_DROPPED;
-    if ((!pts_host && n) || !pose || stride < 3) return fail(c, PCF_ERR_INVALID, "bad frame arguments");
+// H2D copy of one host cloud into the device staging ring + the integration launch behind it.  `slot_done`, when given,
+// is recorded on the copy stream after the copy (the pinned source may be refilled once it has fired).
+static int push_host_cloud_impl(pcf_ctx* c, const void* src_host, size_t bytes, size_t first_float, uint32_t n, uint32_t stride,
+                                const RowLayout* rows, const double pose[16], const float* explicit_vp, uint32_t frame_idx,
+                                uint32_t n_offered, cudaEvent_t slot_done) {
     int rc = check_frame_idx(c, frame_idx, 1);
     if (rc) return rc;
-    CU(cudaSetDevice(c->device));
     if ((rc = flush_holders(c))) return rc;
     uint32_t chunks = div_up(n, kWChunk);
     if ((uint64_t)c->n_chunks + chunks > kMaxChunks) return fail(c, PCF_ERR_CAPACITY, "point log limit reached");
     if ((rc = ensure_log(c, c->n_chunks + chunks))) return rc;
     int s = c->ring_pos;
     c->ring_pos = (c->ring_pos + 1) % kRing;
-    size_t bytes = (size_t)n * stride * 4;
     if (bytes > c->stage_cap[s]) {
         CU(cudaEventSynchronize(c->ev_free[s]));
         if (c->stage[s]) CU(cudaFree(c->stage[s]));
@@ -728,13 +794,17 @@ static int push_host_cloud(pcf_ctx* c, const float* pts_host, uint32_t n, uint32
     }
     // copy stream: wait until the kernel that last read this slot is done, then upload
     CU(cudaStreamWaitEvent(c->copy_stream, c->ev_free[s], 0));
-    if (bytes) CU(cudaMemcpyAsync(c->stage[s], pts_host, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    if (bytes) CU(cudaMemcpyAsync(c->stage[s], src_host, bytes, cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaEventRecord(c->ev_copied[s], c->copy_stream));
-    c->uploads++;
-    CU(cudaEventRecord(c->ev_upload[c->uploads % kTickets], c->copy_stream));
+    if (slot_done) {
+        CU(cudaEventRecord(slot_done, c->copy_stream));
+    } else {
+        c->uploads++;
+        CU(cudaEventRecord(c->ev_upload[c->uploads % kTickets], c->copy_stream));
+    }
     CU(cudaStreamWaitEvent(c->stream, c->ev_copied[s], 0));
     if (chunks) {
-        rc = launch_ingest(c, c->stage[s], 0, n, 1, stride, pose, frame_idx, explicit_vp);
+        rc = launch_ingest(c, c->stage[s] + first_float, 0, n, 1, stride, pose, frame_idx, explicit_vp, rows);
         if (rc) return rc;
     }
     CU(cudaEventRecord(c->ev_free[s], c->stream));
@@ -742,42 +812,135 @@ static int push_host_cloud(pcf_ctx* c, const float* pts_host, uint32_t n, uint32
     c->occ_dirty = true;
     c->sorted_valid = false;
     c->stats.frames_pushed++;
-    c->stats.points_offered += n;
+    c->stats.points_offered += n_offered;
     c->stats.h2d_bytes += bytes;
     return PCF_OK;
+}
+
+static int push_host_cloud(pcf_ctx* c, const float* pts_host, uint32_t n, uint32_t stride, const double pose[16],
+                           const float* explicit_vp, uint32_t frame_idx) {
+    if (!c) return PCF_ERR_INVALID;
+    if (!c->started) return PCF_DROPPED;
+    if ((!pts_host && n) || !pose || stride < 3) return fail(c, PCF_ERR_INVALID, "bad frame arguments");
+    ENTER(c);
+    const size_t bytes = (size_t)n * stride * 4;          // pts_host is an [n, stride] float array
+    return push_host_cloud_impl(c, pts_host, bytes, 0, n, stride, nullptr, pose, explicit_vp, frame_idx, n, nullptr);
 }
 
 int pcf_push_frame(pcf_ctx* c, const float* pts_host, uint32_t n, uint32_t stride, const double pose[16], uint32_t frame_idx) {
     return push_host_cloud(c, pts_host, n, stride, pose, nullptr, frame_idx);
 }
 
-// sensor_msgs/PointCloud2 front end (node.cpp:182-216): x, y, z are consecutive float32 fields `x_offset` bytes into
-// every `point_step`-byte point.  Unlike the reference, which walks only the first `row_step` bytes (D6), every row
-// of an organized cloud is integrated.  The bytes are uploaded as they are; the kernel strides over them.
-int pcf_push_pointcloud2(pcf_ctx* c, const uint8_t* data, uint32_t width, uint32_t height, uint32_t point_step, uint32_t row_step,
-                         uint32_t x_offset, uint32_t y_offset, uint32_t z_offset, const double pose[16], uint32_t frame_idx) {
-    if (!c) return PCF_ERR_INVALID;
+static int check_pointcloud2(pcf_ctx* c, const uint8_t* data, uint32_t width, uint32_t height, uint32_t point_step, uint32_t row_step,
+                             uint32_t x_offset, uint32_t y_offset, uint32_t z_offset, const double* pose) {
     if (!data || !pose) return fail(c, PCF_ERR_INVALID, "null cloud / pose");
     if (point_step % 4 || x_offset % 4 || y_offset != x_offset + 4 || z_offset != x_offset + 8 || point_step < x_offset + 12)
         return fail(c, PCF_ERR_INVALID, "PointCloud2 layout not supported: x, y, z must be consecutive 4-byte aligned float32 fields");
-    if (row_step < (uint64_t)width * point_step) return fail(c, PCF_ERR_INVALID, "row_step smaller than width * point_step");
-    const uint64_t n = (uint64_t)width * height;
-    if (n > 0xFFFFFFFFull) return fail(c, PCF_ERR_INVALID, "cloud too large");
-    const float* first = reinterpret_cast<const float*>(data + x_offset);
-    if (row_step == (uint64_t)width * point_step || height <= 1)
-        return push_host_cloud(c, first, (uint32_t)n, point_step / 4, pose, nullptr, frame_idx);
-    // padded rows: squeeze the padding out on the host (rare; drivers emit dense rows)
-    std::vector<uint8_t> dense((size_t)n * point_step);
-    for (uint32_t r = 0; r < height; r++) memcpy(dense.data() + (size_t)r * width * point_step, data + (size_t)r * row_step, (size_t)width * point_step);
-    int rc = push_host_cloud(c, reinterpret_cast<const float*>(dense.data() + x_offset), (uint32_t)n, point_step / 4, pose, nullptr, frame_idx);
-    if (rc == PCF_OK) CU(cudaStreamSynchronize(c->copy_stream));     // `dense` dies with this call
-    return rc;
+    if (row_step < (uint64_t)width * point_step || row_step % 4) return fail(c, PCF_ERR_INVALID, "row_step smaller than width * point_step (or not a multiple of 4)");
+    if ((uint64_t)width * height > 0xFFFFFFFFull) return fail(c, PCF_ERR_INVALID, "cloud too large");
+    return PCF_OK;
+}
+
+// sensor_msgs/PointCloud2 front end (node.cpp:182-216): x, y, z are consecutive float32 fields `x_offset` bytes into
+// every `point_step`-byte point, rows are `row_step` bytes apart.  Unlike the reference, which walks only the first
+// `row_step` bytes (D6), every row of an organized cloud is integrated.  The message bytes are uploaded as they are --
+// [data, last z of the last point], never a byte more -- and the kernel strides over points and rows.
+int pcf_push_pointcloud2(pcf_ctx* c, const uint8_t* data, uint32_t width, uint32_t height, uint32_t point_step, uint32_t row_step,
+                         uint32_t x_offset, uint32_t y_offset, uint32_t z_offset, const double pose[16], uint32_t frame_idx) {
+    if (!c) return PCF_ERR_INVALID;
+    int rc = check_pointcloud2(c, data, width, height, point_step, row_step, x_offset, y_offset, z_offset, pose);
+    if (rc) return rc;
+    if (!c->started) return PCF_DROPPED;
+    ENTER(c);
+    const uint32_t n = width * height;
+    const bool dense_rows = row_step == (uint64_t)width * point_step || height <= 1;
+    const size_t bytes = n ? (size_t)(height - 1) * row_step + (size_t)(width - 1) * point_step + x_offset + 12 : 0;
+    if (dense_rows && x_offset == 0)      // plain [n, point_step] array: the fast paths (float4 / packed xyz bulk kernels) apply
+        return push_host_cloud_impl(c, data, (size_t)n * point_step, 0, n, point_step / 4, nullptr, pose, nullptr, frame_idx, n, nullptr);
+    RowLayout rl{dense_rows ? (n ? n : 1u) : width, point_step / 4, row_step / 4};
+    return push_host_cloud_impl(c, data, bytes, x_offset / 4, n, 0, &rl, pose, nullptr, frame_idx, n, nullptr);
 }
 
 int pcf_add_points(pcf_ctx* c, const float* pts_host, uint32_t n, uint32_t stride, const float viewpoint[3], uint32_t frame_idx) {
     static const double identity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
     if (!viewpoint) return c ? fail(c, PCF_ERR_INVALID, "null viewpoint") : PCF_ERR_INVALID;
     return push_host_cloud(c, pts_host, n, stride, identity, viewpoint, frame_idx);
+}
+
+// ---- host staging (node.cpp:218-263): clip-and-pack on the host, so that only the clipped cloud crosses PCIe ----------
+int pcf_stage_frame(pcf_ctx* c, const float* pts_host, uint32_t n, uint32_t stride, float* staged_xyz, uint32_t* n_staged) {
+    if (!c || !staged_xyz || !n_staged || (!pts_host && n) || stride < 3) return c ? fail(c, PCF_ERR_INVALID, "bad staging arguments") : PCF_ERR_INVALID;
+    StageJob j;
+    j.data = reinterpret_cast<const uint8_t*>(pts_host);
+    j.rows = 1; j.cols = n; j.row_step = 0; j.point_step = stride * 4; j.x_offset = 0;
+    *n_staged = clip_pack(j, c->g.clip_lo, c->g.clip_hi, staged_xyz);
+    return PCF_OK;
+}
+
+static int ensure_stager(pcf_ctx* c) {
+    if (c->stager) return PCF_OK;
+    int threads = c->cfg.stage_threads;
+    if (const char* e = getenv("PCF_STAGE_THREADS")) if (atoi(e) > 0) threads = atoi(e);
+    if (threads <= 0) threads = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+    Stager::Hooks h;
+    const int dev = c->device;
+    h.alloc_pinned = [](size_t bytes) { return pcf_host_alloc(bytes); };
+    h.free_pinned = [](void* p) { pcf_host_free(p); };
+    h.thread_init = [dev](int) { cudaSetDevice(dev); };
+    h.slot_wait = [c](int s) { cudaEventSynchronize(c->slot_ev[s]); };
+    h.push = [c](int s, const float* xyz, uint32_t n_staged, uint32_t n_offered, const double* pose, uint32_t frame_idx) {
+        return push_host_cloud_impl(c, xyz, (size_t)n_staged * 12, 0, n_staged, 3, nullptr, pose, nullptr, frame_idx, n_offered, c->slot_ev[s]);
+    };
+    c->slot_ev.assign((size_t)threads * 2, nullptr);
+    for (cudaEvent_t& e : c->slot_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->stager.reset(new Stager(threads, c->g.clip_lo, c->g.clip_hi, std::move(h)));
+    return PCF_OK;
+}
+
+static int submit_job(pcf_ctx* c, StageJob& j, const double pose[16], uint32_t frame_idx) {
+    if (!c->started) return PCF_DROPPED;                     // node.cpp:329-331
+    CU(cudaSetDevice(c->device));
+    int rc = ensure_stager(c);
+    if (rc) return rc;
+    memcpy(j.pose, pose, sizeof j.pose);
+    j.frame_idx = frame_idx;
+    c->stager->submit(j);                                    // node.cpp:345-347
+    return PCF_OK;
+}
+
+int pcf_submit_frame(pcf_ctx* c, const float* pts_host, uint32_t n, uint32_t stride, const double pose[16], uint32_t frame_idx) {
+    if (!c) return PCF_ERR_INVALID;
+    if ((!pts_host && n) || !pose || stride < 3) return fail(c, PCF_ERR_INVALID, "bad frame arguments");
+    StageJob j;
+    j.data = reinterpret_cast<const uint8_t*>(pts_host);
+    j.rows = 1; j.cols = n; j.row_step = 0; j.point_step = stride * 4; j.x_offset = 0;
+    return submit_job(c, j, pose, frame_idx);
+}
+
+int pcf_submit_pointcloud2(pcf_ctx* c, const uint8_t* data, uint32_t width, uint32_t height, uint32_t point_step, uint32_t row_step,
+                           uint32_t x_offset, uint32_t y_offset, uint32_t z_offset, const double pose[16], uint32_t frame_idx) {
+    if (!c) return PCF_ERR_INVALID;
+    int rc = check_pointcloud2(c, data, width, height, point_step, row_step, x_offset, y_offset, z_offset, pose);
+    if (rc) return rc;
+    StageJob j;
+    j.data = data;
+    j.rows = height; j.cols = width; j.row_step = row_step; j.point_step = point_step; j.x_offset = x_offset;
+    return submit_job(c, j, pose, frame_idx);
+}
+
+int pcf_drain(pcf_ctx* c) {
+    if (!c) return PCF_ERR_INVALID;
+    return drain_staged(c);
+}
+int pcf_staged_count(pcf_ctx* c, uint64_t* n) {
+    if (!c || !n) return PCF_ERR_INVALID;
+    *n = c->stager ? c->stager->staged() : 0;
+    return PCF_OK;
+}
+int pcf_wait_staged(pcf_ctx* c, uint64_t n) {
+    if (!c) return PCF_ERR_INVALID;
+    if (c->stager) c->stager->wait_staged(n);
+    return PCF_OK;
 }
 
 int pcf_upload_ticket(pcf_ctx* c, uint64_t* ticket) {
@@ -807,9 +970,9 @@ int pcf_push_frames_device(pcf_ctx* c, const float* pts_dev, uint32_t n_frames, 
     if (!c->started) return PCF_DROPPED;
     if (!n_frames) return PCF_OK;
     if (!pts_dev || !poses || stride < 3) return fail(c, PCF_ERR_INVALID, "bad frame arguments");
+    ENTER(c);
     int rc = check_frame_idx(c, first_frame_idx, n_frames);
     if (rc) return rc;
-    CU(cudaSetDevice(c->device));
     if ((rc = flush_holders(c))) return rc;
     uint32_t chunks = div_up(n_per_frame, kWChunk);
     if ((uint64_t)c->n_chunks + (uint64_t)chunks * n_frames > kMaxChunks) return fail(c, PCF_ERR_CAPACITY, "point log limit reached");
@@ -832,7 +995,7 @@ int pcf_push_frames_device(pcf_ctx* c, const float* pts_dev, uint32_t n_frames, 
 
 int pcf_sync(pcf_ctx* c) {
     if (!c) return PCF_ERR_INVALID;
-    CU(cudaSetDevice(c->device));
+    ENTER(c);
     CU(cudaStreamSynchronize(c->copy_stream));
     CU(cudaStreamSynchronize(c->stream));
     return PCF_OK;
@@ -840,7 +1003,7 @@ int pcf_sync(pcf_ctx* c) {
 
 int pcf_count_kept(pcf_ctx* c, uint64_t* kept) {
     if (!c || !kept) return PCF_ERR_INVALID;
-    CU(cudaSetDevice(c->device));
+    ENTER(c);
     CU(cudaStreamSynchronize(c->copy_stream));
     uint32_t P = 0;
     if (c->n_chunks) {
@@ -859,7 +1022,7 @@ int pcf_count_kept(pcf_ctx* c, uint64_t* kept) {
 
 int pcf_update(pcf_ctx* c) {
     if (!c) return PCF_ERR_INVALID;
-    CU(cudaSetDevice(c->device));
+    ENTER(c);
     CU(cudaEventRecord(c->ev_a, c->stream));
     int rc = flush_holders(c);
     if (rc) return rc;
@@ -917,20 +1080,20 @@ int pcf_update(pcf_ctx* c) {
 
 int pcf_extract(pcf_ctx* c, pcf_result* out) {
     if (!c) return PCF_ERR_INVALID;
-    CU(cudaSetDevice(c->device));
+    ENTER(c);
     return extract_impl(c, 0, out);
 }
 
 int pcf_extract_hq(pcf_ctx* c, double threshold, pcf_result* out) {
     if (!c) return PCF_ERR_INVALID;
-    CU(cudaSetDevice(c->device));
+    ENTER(c);
     // downloadHQ skips `count < threshold` (OG.hpp:561): for an int count that is count >= ceil(threshold)
     return extract_impl(c, (int32_t)std::ceil(threshold), out);
 }
 
 int pcf_clear(pcf_ctx* c) {
     if (!c) return PCF_ERR_INVALID;
-    CU(cudaSetDevice(c->device));
+    ENTER(c);
     CU(cudaStreamSynchronize(c->copy_stream));
     int rc = reset_grid_state(c);
     if (rc) return rc;
@@ -952,7 +1115,7 @@ int pcf_dump_state(pcf_ctx* c, pcf_state* out) {
     if (!c || !out) return PCF_ERR_INVALID;
     memset(out, 0, sizeof *out);
     if (c->slab_hi >= 0) return fail(c, PCF_ERR_INVALID, "pcf_dump_state needs the whole grid (an x-slab is set)");
-    CU(cudaSetDevice(c->device));
+    ENTER(c);
     int rc = run_scoring(c);
     if (rc) return rc;
     size_t n = c->n_vox;
@@ -984,12 +1147,14 @@ int pcf_dump_state(pcf_ctx* c, pcf_state* out) {
 
 int pcf_get_stats(pcf_ctx* c, pcf_stats* out) {
     if (!c || !out) return PCF_ERR_INVALID;
+    c->stats.staged_dropped = c->staged_dropped;
     *out = c->stats;
     return PCF_OK;
 }
 int pcf_reset_stats(pcf_ctx* c) {
     if (!c) return PCF_ERR_INVALID;
     c->stats = pcf_stats{};
+    c->staged_dropped = 0;
     return PCF_OK;
 }
 int pcf_last_timings(pcf_ctx* c, float* update_ms, float* extract_device_ms, float* extract_d2h_ms) {
@@ -1004,9 +1169,11 @@ void* pcf_stream(pcf_ctx* c) { return c ? (void*)c->stream : nullptr; }
 // ---- multi-GPU hooks ---------------------------------------------------------------------------------
 int pcf_grid_buffer(pcf_ctx* c, void** first_frame_dev, uint64_t* n_cells) {
     if (!c || !first_frame_dev || !n_cells) return PCF_ERR_INVALID;
+    ENTER(c);
     *first_frame_dev = c->first_frame;
     *n_cells = c->g.phys_cells;      // bricked physical layout: identical on every rank, so an elementwise reduce is still valid
-    c->occ_dirty = true;        // the caller is about to reduce into it
+    c->occ_dirty = true;        // the caller is about to reduce into it: the occupancy bitmap must be rebuilt from the grid
+    c->occ_from_grid = true;
     c->sorted_valid = false;
     return PCF_OK;
 }
@@ -1018,7 +1185,7 @@ int pcf_viewpoint_table(pcf_ctx* c, void** vp_dev, uint32_t* max_frames) {
 }
 int pcf_log_compact(pcf_ctx* c, void** log_dev, uint64_t* n_points) {
     if (!c || !log_dev || !n_points) return PCF_ERR_INVALID;
-    CU(cudaSetDevice(c->device));
+    ENTER(c);
     CU(cudaStreamSynchronize(c->copy_stream));
     *log_dev = nullptr;
     *n_points = 0;
@@ -1055,7 +1222,8 @@ int pcf_log_replace(pcf_ctx* c, const void* log_dev, uint64_t n_points) {
     if (!c || (!log_dev && n_points)) return PCF_ERR_INVALID;
     if (n_points >= 0xFFFFFFFFull) return fail(c, PCF_ERR_CAPACITY, "merged log too large");
     if (c->n_normals) return fail(c, PCF_ERR_INVALID, "pcf_log_replace after pcf_update: sharded merge of interleaved schedules is not supported");
-    CU(cudaSetDevice(c->device));
+    ENTER(c);
+    c->log_installed = true;
     CU(cudaStreamSynchronize(c->copy_stream));
     const float4* in = (const float4*)log_dev;
     // keep the records of this context's x-slab plus the reach of the +-K walk (OG.hpp:403-405): walk_k cells
@@ -1096,7 +1264,7 @@ int pcf_log_replace(pcf_ctx* c, const void* log_dev, uint64_t n_points) {
 
 int pcf_plane_counts(pcf_ctx* c, uint32_t* counts_host) {
     if (!c || !counts_host) return PCF_ERR_INVALID;
-    CU(cudaSetDevice(c->device));
+    ENTER(c);
     int rc = build_occupancy(c);
     if (rc) return rc;
     uint32_t np = c->g.n1[0];
@@ -1111,9 +1279,11 @@ int pcf_plane_counts(pcf_ctx* c, uint32_t* counts_host) {
 // ---- exchange v2: slab-routed records, compaction fused with the (peer) write ---------------------------------
 int pcf_plane_point_counts(pcf_ctx* c, uint32_t* counts_host) {
     if (!c || !counts_host) return PCF_ERR_INVALID;
-    CU(cudaSetDevice(c->device));
+    ENTER(c);
     CU(cudaStreamSynchronize(c->copy_stream));
     uint32_t np = c->g.n1[0];
+    if ((size_t)np * 4 > 200 * 1024) return fail(c, PCF_ERR_INVALID, "pcf_plane_point_counts: %u x-planes exceed the shared-memory histogram (51200)", np);
+    if ((size_t)np * 4 > 48 * 1024) CU(cudaFuncSetAttribute(k_plane_point_counts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)np * 4));
     int rc = reserve(c, c->tmpA, (size_t)np * 4);
     if (rc) return rc;
     CU(cudaMemsetAsync(c->tmpA.p, 0, (size_t)np * 4, c->stream));
@@ -1130,9 +1300,10 @@ int pcf_plane_point_counts(pcf_ctx* c, uint32_t* counts_host) {
 
 int pcf_exchange_counts(pcf_ctx* c, const int32_t* bounds, int32_t n_ranks, uint64_t* counts_host) {
     if (!c || !bounds || !counts_host || n_ranks < 1 || n_ranks > kMaxRanks) return c ? fail(c, PCF_ERR_INVALID, "bad exchange arguments (1..%d ranks)", kMaxRanks) : PCF_ERR_INVALID;
-    CU(cudaSetDevice(c->device));
+    ENTER(c);
     CU(cudaStreamSynchronize(c->copy_stream));
     if (c->n_normals) return fail(c, PCF_ERR_INVALID, "exchange after pcf_update: sharded merge of interleaved schedules is not supported");
+    if (c->log_installed) return fail(c, PCF_ERR_INVALID, "exchange after pcf_install_records / pcf_log_replace: the installed log has lost its per-chunk frame indices; pcf_clear first");
     const int32_t halo = std::max(c->g.walk_k, 2);      // +-K walk (OG.hpp:403-405) and the 5x5x5 scan (OG.hpp:334)
     ExchangePlan& p = c->plan;
     p.n_ranks = (uint32_t)n_ranks;
@@ -1257,7 +1428,8 @@ int pcf_install_records(pcf_ctx* c, const void* records_dev, uint64_t n) {
     if (!c || (!records_dev && n)) return PCF_ERR_INVALID;
     if (n >= 0xFFFFFFFFull) return fail(c, PCF_ERR_CAPACITY, "merged log too large");
     if (c->n_normals) return fail(c, PCF_ERR_INVALID, "pcf_install_records after pcf_update: sharded merge of interleaved schedules is not supported");
-    CU(cudaSetDevice(c->device));
+    ENTER(c);
+    c->log_installed = true;
     CU(cudaStreamSynchronize(c->copy_stream));
     uint32_t chunks = div_up(n, kWChunk);
     if (chunks > kMaxChunks) return fail(c, PCF_ERR_CAPACITY, "point log limit reached");
@@ -1265,8 +1437,9 @@ int pcf_install_records(pcf_ctx* c, const void* records_dev, uint64_t n) {
     int rc = ensure_log(c, std::max<uint32_t>(chunks, 1));
     if (rc) return rc;
     LAUNCH(c, k_fill_u32, 148 * 8, 512, c->first_frame, c->g.phys_cells, kEmpty);
+    CU(cudaMemsetAsync(c->occ_bits, 0, (c->n_words + 2) * 4, c->stream));
     if (n) {
-        LAUNCH(c, k_install_records, div_up(n, kBlock), kBlock, (const float4*)records_dev, n, c->g, c->first_frame, c->log);
+        LAUNCH(c, k_install_records, div_up(n, kBlock), kBlock, (const float4*)records_dev, n, c->g, c->first_frame, c->occ_bits, c->log);
         LAUNCH(c, k_chunk_counts_dense, div_up(chunks, kBlock), kBlock, c->chunk_count, chunks, n);
         CU(cudaGetLastError());
     }

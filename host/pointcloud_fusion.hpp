@@ -4,19 +4,17 @@
 // Same service semantics, ROS removed:
 //   onReceivedPointCloud()  node.cpp:327-349  enqueue a (cloud, pose) pair while `start_` is set, drop it otherwise
 //   start() / stop()        node.cpp:361-375  flip the gate; frames already queued keep integrating
-//   reset()                 node.cpp:351-359  drop the not-yet-integrated input, keep the grid
+//   reset()                 node.cpp:351-359  start_ = false, drop the not-yet-staged input, keep the grid
 //   getFusedCloud()         node.cpp:377-440  drain, write <dir>/test_cloud.pcd + <dir>/meta.csv, clear the grid
-// What the three worker threads + two mutex-protected deques of the reference (node.cpp:130-143,218-325) did on the
-// CPU is now: one pool of PINNED staging slots (filled by the producer), one worker thread that hands every queued
-// slot to pcf_push_frame (async H2D + the integration kernel on the context's CUDA streams), and an explicit
-// update schedule instead of the 5 s cleanGrid timer (D4): `update_every` frames, plus once at process().
+// The reference's pipeline -- clouds_ deque -> addPoints thread (decode + depth clip) -> clouds_processed_ deque ->
+// updateStates thread (transform + grid insert), node.cpp:130-143,218-299 -- maps onto the library's staging pool
+// (pcf_submit_frame: queue -> clip-and-pack threads -> pinned slots -> in-order H2D + integration kernel), so this
+// class owns no thread of its own: every call comes from the caller's thread and one context is never driven from two
+// threads at once.  The 5 s cleanGrid timer (node.cpp:301-325) becomes an explicit schedule (D4): `update_every`
+// frames, plus once at process().
 #pragma once
-#include <condition_variable>
 #include <cstdint>
-#include <deque>
-#include <mutex>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "../include/pcfusion.h"
@@ -32,8 +30,9 @@ class PointcloudFusion {
         std::string directory_name = ".";                   // launch:6
         int device = 0;
         int update_every = 0;        // run updateThicknessVectors after every k integrated frames (0: only at process)
-        uint32_t staging_slots = 8;  // pinned slots = frames that can be in flight (the reference queues up to 100 messages, node.cpp:152)
+        uint32_t staging_slots = 8;  // caller-side cloud buffers that can be in flight (the reference queues up to 100 messages, node.cpp:152)
         uint64_t log_capacity_hint = 0;
+        int stage_threads = 0;       // host staging threads inside the library (0: auto)
     };
     struct Counters {
         uint64_t received = 0, dropped = 0, integrated = 0, discarded_by_reset = 0, updates = 0;
@@ -44,11 +43,13 @@ class PointcloudFusion {
     bool ok() const { return ctx_ != nullptr; }
     const std::string& last_error() const { return err_; }
 
-    // Zero-copy producer interface: get a pinned slot able to hold `floats` floats (blocks while all slots are in
-    // flight), fill it, submit it.  submit() returns false when the frame was dropped because fusion is stopped.
+    // Producer interface without an extra copy: get a cloud buffer able to hold `floats` floats (blocks while all of
+    // them are still being staged), fill it, submit it.  submit() returns false when the frame was dropped because
+    // fusion is stopped.
     float* acquire(size_t floats);
     bool submit(float* slot, uint32_t n_points, uint32_t stride_floats, const double pose[16]);
-    // node.cpp:327-349: copying variant for callers that own their cloud memory
+    // node.cpp:327-349: variant for callers that own their cloud memory.  The cloud is read by the staging threads
+    // after this call returns: it must stay valid until drain() (a ROS bridge holds the message pointer that long).
     bool onReceivedPointCloud(const float* xyz, uint32_t n_points, uint32_t stride_floats, const double pose[16]);
 
     bool reset();          // node.cpp:351-359
@@ -62,20 +63,18 @@ class PointcloudFusion {
     float last_process_ms() const { return process_ms_; }
 
    private:
-    struct Slot { float* p = nullptr; size_t cap = 0; uint64_t ticket = 0; bool busy = false; };
-    struct Item { int slot; uint32_t n, stride; double pose[16]; };
-    void worker();
+    struct Slot { float* p = nullptr; size_t cap = 0; uint64_t staged_at = 0; bool busy = false; };
+    bool push(const float* xyz, uint32_t n, uint32_t stride, const double pose[16]);
 
     Params prm_;
     pcf_ctx* ctx_ = nullptr;
     std::string err_;
     std::vector<Slot> slots_;
-    std::deque<Item> clouds_;             // node.cpp:137
-    std::mutex mtx_;                      // node.cpp:140
-    std::condition_variable cv_work_, cv_free_, cv_idle_;
-    std::thread thread_;
-    bool start_ = false, quit_ = false, busy_ = false;
+    size_t next_slot_ = 0;
+    uint64_t submitted_ = 0;      // clouds accepted by pcf_submit_frame since the last reset (the pool hands them over in this order)
+    uint64_t base_ = 0;           // pcf_staged_count at the last reset
     uint32_t next_frame_ = 0;
+    uint64_t since_update_ = 0;
     Counters cnt_;
     float process_ms_ = 0.f;
 };

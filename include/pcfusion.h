@@ -55,6 +55,8 @@ typedef struct {
     int32_t device;              /* CUDA device ordinal */
     uint32_t max_frames;         /* size of the frame/viewpoint table (frame_idx < max_frames) */
     uint64_t log_capacity_hint;  /* initial point-log capacity in INPUT points; grows on demand */
+    int32_t stage_threads;       /* host staging threads of pcf_submit_* (the reference has ONE addPoints thread,
+                                    node.cpp:166,218); 0 = min(16, hardware threads); env PCF_STAGE_THREADS overrides */
 } pcf_config;
 
 /* Extraction output, structure of arrays, x-major voxel order = the reference's scan order
@@ -91,6 +93,7 @@ typedef struct {
     uint64_t kernel_launches;     /* library kernels launched since create / last pcf_reset_stats */
     uint64_t h2d_bytes, d2h_bytes;
     uint32_t update_passes;
+    uint64_t staged_dropped;      /* clouds dropped by pcf_reset before a staging thread took them (node.cpp:356) */
 } pcf_stats;
 
 void pcf_default_config(pcf_config* cfg);       /* launch-file defaults: launch:4-8, node.cpp:91-93 */
@@ -102,7 +105,9 @@ int pcf_dims(const pcf_ctx* ctx, int32_t dims[3]);      /* xdim_,ydim_,zdim_  OG
 /* Service semantics (std_srvs/Trigger handlers). */
 int pcf_start(pcf_ctx* ctx);    /* node.cpp:361-367 */
 int pcf_stop(pcf_ctx* ctx);     /* node.cpp:369-375: queued frames still integrate */
-int pcf_reset(pcf_ctx* ctx);    /* node.cpp:351-359: drops not-yet-integrated input, keeps the grid */
+int pcf_reset(pcf_ctx* ctx);    /* node.cpp:351-359: start_ = false + clouds_.clear(): closes the gate and drops the clouds submitted
+                                   with pcf_submit_* that no staging thread has taken yet; clouds already being staged
+                                   (the reference's clouds_processed_) still integrate; the grid is kept */
 
 /* Frame integration = onReceivedPointCloud -> addPoints thread (z clip) -> updateStates thread
  * (transformPointCloud + OccupancyGrid::addPoints): node.cpp:327-349, 248-255, 288-296, OG.hpp:185-280.
@@ -123,6 +128,33 @@ int pcf_push_pointcloud2(pcf_ctx* ctx, const uint8_t* data, uint32_t width, uint
  * is the faster route that also moves the clip and the transform onto the GPU. */
 int pcf_add_points(pcf_ctx* ctx, const float* pts_host, uint32_t n, uint32_t stride_floats, const float viewpoint[3],
                    uint32_t frame_idx);
+/* ---- host staging = the reference's addPoints() thread (node.cpp:218-263: decode + camera-frame depth clip) -----------
+ * pcf_submit_frame / pcf_submit_pointcloud2 are the asynchronous counterparts of pcf_push_frame / pcf_push_pointcloud2 and
+ * the entry points a live bridge should use: the call only queues the cloud (node.cpp:345-347; it blocks while 4 x
+ * stage_threads clouds are waiting).  A pool of staging threads walks each cloud once, drops the points outside
+ * clip_zmin < z < clip_zmax (node.cpp:251; the same float thresholds the kernel uses, exactly equivalent to the
+ * reference's double compares) and packs the survivors, in point order, as 12-byte xyz into pinned slots; slots are
+ * uploaded and integrated strictly in submission order, so results are bit-identical to pcf_push_frame while only the
+ * clipped cloud crosses PCIe.  `pts_host` / `data` may be pageable memory (a ROS message) and must stay valid until the
+ * cloud has been staged: until pcf_drain, or any call that drains (pcf_sync, pcf_count_kept, pcf_update, pcf_extract,
+ * pcf_process, pcf_clear, direct pcf_push_*).  Returns PCF_DROPPED while stopped.  Errors of the deferred integration
+ * surface at the next draining call. */
+int pcf_submit_frame(pcf_ctx* ctx, const float* pts_host, uint32_t n, uint32_t stride_floats, const double pose[16],
+                     uint32_t frame_idx);
+int pcf_submit_pointcloud2(pcf_ctx* ctx, const uint8_t* data, uint32_t width, uint32_t height, uint32_t point_step,
+                           uint32_t row_step, uint32_t x_offset, uint32_t y_offset, uint32_t z_offset, const double pose[16],
+                           uint32_t frame_idx);
+int pcf_drain(pcf_ctx* ctx);    /* wait until every submitted cloud has been staged and handed to the GPU (not for the GPU) */
+/* Source-buffer bookkeeping for callers that recycle their cloud memory: pcf_staged_count = clouds handed to the GPU by the
+ * pool so far (in submission order; clouds dropped by pcf_reset are not counted); pcf_wait_staged(n) blocks until that count
+ * reaches n or nothing is pending. */
+int pcf_staged_count(pcf_ctx* ctx, uint64_t* n);
+int pcf_wait_staged(pcf_ctx* ctx, uint64_t n);
+/* The clip-and-pack step on its own, on the calling thread, for hosts that run their own staging threads:
+ * staged_xyz (>= 3 * (n + 4) floats, pinned for full upload speed) receives the clipped points as packed xyz, padded
+ * with NaN points to a multiple of 4; pass it to pcf_push_frame(ctx, staged_xyz, *n_staged, 3, pose, frame_idx). */
+int pcf_stage_frame(pcf_ctx* ctx, const float* pts_host, uint32_t n, uint32_t stride_floats, float* staged_xyz,
+                    uint32_t* n_staged);
 /* Pinned (page-locked) host memory for staging clouds: what the reference's deques hold (node.cpp:130-143) lives
  * here so that pcf_push_frame's H2D copy runs at full PCIe speed and asynchronously. */
 void* pcf_host_alloc(size_t bytes);

@@ -199,6 +199,45 @@ struct Voxel {
     VoxelInfo* data = nullptr;
 };
 
+// The reference's grid is a dense vector<vector<vector<Voxel>>> (OG.hpp:108,626): 16 bytes per cell, 16 GB for the
+// 1000^3 grids of C3/C4/C5.  The restatement keeps the same cell semantics (a never-touched cell reads as
+// {occupied=false, data=nullptr}) in 8x8x8-cell pages allocated on first WRITE, so that full-size runs fit any host.
+// Container choice only: tests/test_oracle_golden.py pins it against the reference's own dense header build.
+class PagedVoxels {
+   public:
+    void init(int nx, int ny, int nz) {
+        clear();
+        nx_ = nx; ny_ = ny; nz_ = nz;
+        px_ = (nx + 7) >> 3; py_ = (ny + 7) >> 3; pz_ = (nz + 7) >> 3;
+        table_.assign((size_t)px_ * py_ * pz_, nullptr);
+    }
+    ~PagedVoxels() { clear(); }
+    Voxel& at(int x, int y, int z) {
+        Voxel*& pg = table_[page_of(x, y, z)];
+        if (!pg) pg = new Voxel[512]();
+        return pg[cell_of(x, y, z)];
+    }
+    const Voxel& peek(int x, int y, int z) const {
+        const Voxel* pg = table_[page_of(x, y, z)];
+        return pg ? pg[cell_of(x, y, z)] : empty_;
+    }
+    bool page_empty(int x, int y, int z) const { return table_[page_of(x, y, z)] == nullptr; }
+    void clear() {
+        for (Voxel* p : table_) delete[] p;
+        table_.clear();
+    }
+    int nx() const { return nx_; }
+    int ny() const { return ny_; }
+    int nz() const { return nz_; }
+
+   private:
+    size_t page_of(int x, int y, int z) const { return ((size_t)(x >> 3) * py_ + (size_t)(y >> 3)) * pz_ + (size_t)(z >> 3); }
+    static int cell_of(int x, int y, int z) { return ((x & 7) << 6) | ((y & 7) << 3) | (z & 7); }
+    int nx_ = 0, ny_ = 0, nz_ = 0, px_ = 0, py_ = 0, pz_ = 0;
+    std::vector<Voxel*> table_;
+    Voxel empty_{};
+};
+
 struct Result {
     std::vector<uint64_t> hash;
     std::vector<float> centroid, normal, sd;  // 3 per entry
@@ -214,7 +253,7 @@ struct Grid {
     int reserve_hint = 0;
     int walk_k = 3;          // K of updateThicknessVectors<N,K> (node.cpp:311)
     int min_neighbours = 20; // OG.hpp:352
-    std::vector<std::vector<std::vector<Voxel>>> voxels;
+    PagedVoxels voxels;   // (xdim+1) x (ydim+1) x (zdim+1) cells, OG.hpp:626
     std::unordered_set<uint64_t> unprocessed, processed;
     std::vector<VoxelInfo*> all_infos;  // ownership (lets clear() free holders too, D5)
     int dx[125], dy[125], dz[125];
@@ -233,7 +272,7 @@ struct Grid {
         xdim = (int)((xmax - xmin) / xres);
         ydim = (int)((ymax - ymin) / yres);
         zdim = (int)((zmax - zmin) / zres);
-        voxels.assign(xdim + 1, std::vector<std::vector<Voxel>>(ydim + 1, std::vector<Voxel>(zdim + 1)));
+        voxels.init(xdim + 1, ydim + 1, zdim + 1);
     }
     ~Grid() { for (VoxelInfo* p : all_infos) delete p; }
 
@@ -300,7 +339,7 @@ struct Grid {
             int x, y, z;
             voxel_coords(pt, x, y, z);
             uint64_t hash = hash_id(x, y, z);
-            Voxel& vox = voxels[x][y][z];
+            Voxel& vox = voxels.at(x, y, z);
             inserted++;
             if (vox.occupied) {
                 VoxelInfo* d = vox.data;
@@ -321,7 +360,7 @@ struct Grid {
             for (size_t i = 0; i < nd; i++) {
                 int xx, yy, zz;
                 hash_coords(d->dependants[i], xx, yy, zz);
-                VoxelInfo* dep = voxels[xx][yy][zz].data;
+                VoxelInfo* dep = voxels.peek(xx, yy, zz).data;
                 score(dep, pt, voxel_center(xx, yy, zz));
             }
         }
@@ -354,14 +393,14 @@ struct Grid {
         for (uint64_t key : keys) {
             int x, y, z;
             hash_coords(key, x, y, z);
-            Voxel& vox = voxels[x][y][z];
+            const Voxel& vox = voxels.peek(x, y, z);
             if (!vox.occupied) continue;
             VoxelInfo* data = vox.data;
             int total = 0;
             centres.clear();
             for (int d = 0; d < 125; d++) {
                 int i = dx[d], j = dy[d], k = dz[d];
-                if (valid_coord(x + i, y + j, z + k) && voxels[x + i][y + j][z + k].occupied) {
+                if (valid_coord(x + i, y + j, z + k) && voxels.peek(x + i, y + j, z + k).occupied) {
                     centres.push_back(voxel_center(x + i, y + j, z + k));
                     total++;
                 }
@@ -384,7 +423,7 @@ struct Grid {
                 int xx, yy, zz;
                 voxel_coords(q, xx, yy, zz);
                 if (!valid_coord(xx, yy, zz)) continue;
-                Voxel& nb = voxels[xx][yy][zz];
+                Voxel& nb = voxels.at(xx, yy, zz);
                 if (nb.occupied) {
                     nb.data->dependants.push_back(hash);
                     // copy: the reference iterates `for(auto pt: neighbor_data->buffer)` and the
@@ -405,7 +444,8 @@ struct Grid {
         for (int x = 0; x < xdim; x++)
             for (int y = 0; y < ydim; y++)
                 for (int z = 0; z < zdim; z++) {
-                    const Voxel& v = voxels[x][y][z];
+                    if ((z & 7) == 0 && voxels.page_empty(x, y, z)) { z += 7; continue; }
+                    const Voxel& v = voxels.peek(x, y, z);
                     if (!v.occupied || !v.data->normal_found) continue;
                     const VoxelInfo* d = v.data;
                     result.hash.push_back(hash_id(x, y, z));
@@ -421,9 +461,7 @@ struct Grid {
 
     // OG.hpp:167-183 + D5
     void clear() {
-        for (auto& a : voxels)
-            for (auto& b : a)
-                for (auto& v : b) { v.occupied = false; v.data = nullptr; }
+        voxels.init(xdim + 1, ydim + 1, zdim + 1);
         for (VoxelInfo* p : all_infos) delete p;
         all_infos.clear();
         unprocessed.clear();
@@ -475,7 +513,12 @@ void ora_clear(void* g) { ((Grid*)g)->clear(); }
 int64_t ora_state_size(void* g) {
     Grid* G = (Grid*)g;
     int64_t n = 0;
-    for (auto& a : G->voxels) for (auto& b : a) for (auto& v : b) n += v.occupied ? 1 : 0;
+    for (int x = 0; x <= G->xdim; x++)
+        for (int y = 0; y <= G->ydim; y++)
+            for (int z = 0; z <= G->zdim; z++) {
+                if ((z & 7) == 0 && G->voxels.page_empty(x, y, z)) { z += 7; continue; }
+                n += G->voxels.peek(x, y, z).occupied ? 1 : 0;
+            }
     return n;
 }
 void ora_get_state(void* g, uint64_t* hash, int32_t* buffer_len, uint8_t* normal_found, int32_t* count,
@@ -485,7 +528,8 @@ void ora_get_state(void* g, uint64_t* hash, int32_t* buffer_len, uint8_t* normal
     for (int x = 0; x <= G->xdim; x++)
         for (int y = 0; y <= G->ydim; y++)
             for (int z = 0; z <= G->zdim; z++) {
-                const ora::Voxel& v = G->voxels[x][y][z];
+                if ((z & 7) == 0 && G->voxels.page_empty(x, y, z)) { z += 7; continue; }
+                const ora::Voxel& v = G->voxels.peek(x, y, z);
                 if (!v.occupied) continue;
                 hash[n] = Grid::hash_id(x, y, z);
                 buffer_len[n] = (int32_t)v.data->buffer.size();

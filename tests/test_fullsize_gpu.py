@@ -1,10 +1,12 @@
-"""BASELINE.json's configurations at (or near) full size on the GPU.
+"""BASELINE.json's configurations at their named grid sizes on the GPU, every one compared BIT FOR BIT with the CPU oracle.
 
-C1 (20 x 640x480, 1 mm, 0.5 m box) is compared bit for bit with the CPU oracle in full.  The larger grids
-(1 m box @ 1 mm and 0.5 m box @ 0.5 mm = 1000^3 cells, where the oracle's dense CPU grid would need > 16 GB) are
-covered through size-independent properties: strict x-major order of the extraction, conservation of points
-(sum of per-voxel buffer lengths == points that passed clip + crop), idempotent extraction, clear() -> empty, and
-equality of a frame-sharded run (ranks emulated as contexts) with the single-context run."""
+C1 (20 frames) and C2 (200 frames, the bench workload) run in full.  The 1000^3-cell grids (1 m box @ 1 mm: C3, C5;
+0.5 m box @ 0.5 mm: C4) exercise the 30-bit sort-key plan, the 4.3 GB bricked first-frame grid and log slots beyond
+2^28 that the 500^3 grid never reaches; the oracle keeps its cells in lazily allocated pages (same semantics as the
+reference's dense vector, oracle/occupancy_grid_oracle.cpp PagedVoxels), so it runs them on any host in seconds.
+State (occupied set, buffer lengths, normal_found, counts, normals, viewpoints) and extraction are compared with
+tests/helpers.py; the size-independent properties (x-major order, conservation of points, idempotence) stay as well.
+C3 in full (1000 frames) is run once per round by tools/run_configs.py --oracle (profiles/r02_c3_full_oracle.json)."""
 import importlib
 
 import numpy as np
@@ -69,19 +71,57 @@ def test_c1_replay20_bit_exact_vs_oracle(pcf, oracle):
     fus.close()
 
 
-def test_c3_one_metre_box_properties_and_sharding(pcf):
-    """1 m box @ 1 mm = 1000^3 cells (4 GB grid): 24 frames of the plate sweep; sharded x3 == single context."""
+def _gen(scene, frames):
+    import concurrent.futures as cf
+    import os
+    with cf.ThreadPoolExecutor(min(16, os.cpu_count() or 4)) as ex:
+        out = list(ex.map(scene.frame, frames))
+    return np.stack([o[0] for o in out]), np.stack([o[1] for o in out])
+
+
+def test_c2_turntable200_bit_exact_vs_oracle(pcf, oracle):
+    """The bench workload itself (BASELINE configs[1]): 200 x 640x480, two elevation rings, one 200-frame launch."""
+    import torch
+    scene = _synth(pcf).sphere_turntable(200, rings=2)
+    g = scene.grid
+    pts, poses = _gen(scene, range(200))
+    fus = pcf.Fusion(g.box, g.res, log_capacity_hint=200 * scene.points_per_frame)
+    dev = torch.from_numpy(pts).cuda()
+    fus.push_frames_device(dev, 200, scene.points_per_frame, 4, poses, 0)
+    og = oracle.OracleGrid(g.box, g.res)
+    kept = sum(og.add_frame(pts[i], poses[i]) for i in range(200))
+    assert fus.count_kept() == kept and kept > 25_000_000
+    fus.update(); og.update()
+    want = og.download()
+    assert len(want) > 550_000
+    assert_result_parity(fus.extract(), want, "C2 result.")
+    assert_same(fus.state(), og.state(), STATE_FIELDS, "C2 state.")
+    fus.close()
+
+
+def test_c3_one_metre_box_bit_exact_vs_oracle_and_sharding(pcf, oracle):
+    """1 m box @ 1 mm = 1000^3 cells (4.3 GB bricked grid, 30-bit sort keys): 48 frames of the plate sweep (the first raster
+    row and the start of the second, so voxels collect points of non-adjacent frames); oracle bit-exact; sharded x3 == single."""
     sh = importlib.import_module(pcf.__name__ + ".sharded")
     scene = _synth(pcf).plate_sweep(1000)
     g = scene.grid
-    frames = list(range(0, 24))
+    frames = list(range(0, 48))
     one = pcf.Fusion(g.box, g.res)
     assert one.dims == (999, 999, 999)
-    _push_all(one, scene, frames)
+    pts, poses = _push_all(one, scene, frames)
     kept = one.count_kept()
     assert kept > 0.5 * len(frames) * scene.points_per_frame
     one.update()
-    res, _ = _properties(one, kept)
+    res, st = _properties(one, kept)
+    og = oracle.OracleGrid(g.box, g.res)
+    assert og.dims == (999, 999, 999)
+    assert sum(og.add_frame(pts[i], poses[i]) for i in range(len(frames))) == kept
+    og.update()
+    want = og.download()
+    assert len(want) > 300_000
+    assert_result_parity(res, want, "C3 (1000^3) result.")
+    assert_same(st, og.state(), STATE_FIELDS, "C3 (1000^3) state.")
+    og.close()
     ranks = [pcf.Fusion(g.box, g.res) for _ in range(3)]
     for r, f in enumerate(ranks):
         lo, hi = sh.frame_block(len(frames), r, 3)
@@ -92,24 +132,53 @@ def test_c3_one_metre_box_properties_and_sharding(pcf):
         f.close()
 
 
-def test_c4_hires_half_millimetre_interleaved_properties(pcf):
-    """1920x1080 clouds, 0.5 mm voxels (999^3), update after every 2 frames: the incremental dependants path at size."""
+def test_c4_hires_half_millimetre_interleaved_bit_exact_vs_oracle(pcf, oracle):
+    """C4 at its named grid: 1920x1080 clouds, 0.5 m box @ 0.5 mm (999^3), update after every 2 frames -- the incremental
+    dependants path (OG.hpp:244-277) and the holder rule (OG.hpp:443-449) on the 1000^3 layout, against the oracle."""
     scene = _synth(pcf).hires_sphere(6)
     g = scene.grid
-    fus = pcf.Fusion(g.box, g.res)
-    assert fus.dims == (999, 999, 999)
+    fus, og = pcf.Fusion(g.box, g.res), oracle.OracleGrid(g.box, g.res)
+    assert fus.dims == og.dims == (999, 999, 999)
     import torch
+    kept_o = 0
     for i in range(6):
         pts, T = scene.frame(i)
         fus.push_frames_device(torch.from_numpy(pts).cuda(), 1, scene.points_per_frame, 4, T[None], i)
+        kept_o += og.add_frame(pts, T)
         if i % 2 == 1:
-            fus.update()
+            fus.update(); og.update()
     kept = fus.count_kept()
-    fus.update()
+    assert kept == kept_o
+    fus.update(); og.update()
     res, st = _properties(fus, kept, canonical=False)
     assert int(st.buffer_len.sum()) < kept      # points landing in voxels that already have a normal are not buffered (OG.hpp:210-216)
     assert int(res.count.sum()) > 0
-    fus.close()
+    want = og.download()
+    assert len(want) > 500_000
+    assert_result_parity(res, want, "C4 (0.5 mm, 1000^3) result.")
+    assert_same(st, og.state(), STATE_FIELDS, "C4 (0.5 mm, 1000^3) state.")
+    fus.close(); og.close()
+
+
+def test_c5_ten_million_voxels_full_grid_bit_exact_vs_oracle(pcf, oracle):
+    """C5's shape on the full 1 m @ 1 mm grid: 10 one-voxel-thick wavy sheets of 1000 x 1000 voxels (1e7 occupied voxels,
+    1-4 points each) through pcf_add_points (OccupancyGrid::addPoints semantics), update + extraction vs the oracle."""
+    g, sheets = _synth(pcf).wavy_sheets_world(n_sheets=10, n_side=1000)
+    fus = pcf.Fusion(g.box, g.res, log_capacity_hint=sum(len(p) for p, _ in sheets))
+    og = oracle.OracleGrid(g.box, g.res)
+    assert fus.dims == og.dims == (999, 999, 999)
+    kept_o = 0
+    for i, (pts, vp) in enumerate(sheets):
+        fus.add_points(pts, vp, i)
+        kept_o += og.add_points_world(pts, vp)
+    assert fus.count_kept() == kept_o
+    fus.update(); og.update()
+    want = og.download()
+    assert len(want) > 9_000_000
+    got = fus.extract()
+    assert_result_parity(got, want, "C5 (1e7 voxels) result.")
+    assert_same(fus.state(), og.state(), STATE_FIELDS, "C5 (1e7 voxels) state.")
+    fus.close(); og.close()
 
 
 def test_c5_sheets_world_points_bit_exact_vs_oracle(pcf, oracle):

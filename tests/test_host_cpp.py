@@ -110,12 +110,13 @@ def test_replay_driver_matches_oracle(built, sequence, oracle, tmp_path, update_
 
 @pytest.mark.gpu
 def test_replay_reset_discards_only_queued_frames(built, sequence, tmp_path):
-    """reset (node.cpp:351-359) empties the input deque and leaves the grid alone: with everything already handed to the
-    GPU nothing is lost; the accounting must add up either way."""
+    """reset (node.cpp:351-359) sets start_ = false, empties the input deque and leaves the grid alone: the clouds published
+    before it are integrated or discarded, the ones published after it are dropped until the next start."""
     scene, seq = sequence
     r = subprocess.run([REPLAY, seq, "--out", str(tmp_path), "--reset-after", "2", "--slots", "2"], check=True, capture_output=True, text=True)
     line = json.loads(r.stdout.strip().splitlines()[-1])
-    assert line["ok"] and line["integrated"] + line["discarded_by_reset"] == scene.n_frames
+    assert line["ok"] and line["integrated"] + line["discarded_by_reset"] == 3 and line["integrated"] >= 1
+    assert line["dropped"] == scene.n_frames - 3
     assert os.path.getsize(tmp_path / "test_cloud.pcd") > 1000
 
 
