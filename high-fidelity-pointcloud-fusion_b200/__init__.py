@@ -5,4 +5,4 @@ host layer used by the tests, the bench and the multi-GPU replay: a ctypes bindi
 synthetic sequence generator (`synth`) and the frame-sharded multi-GPU merge (`sharded`).
 There is no CPU fallback anywhere in here: without the built library or a CUDA device, calls raise.
 """
-from .binding import Fusion, PcfError, Result, State, lib_path, load_library  # noqa: F401
+from .binding import Fusion, PcfError, Result, State, kat_clip_pack, lib_path, load_library  # noqa: F401

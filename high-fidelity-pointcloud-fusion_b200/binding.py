@@ -50,7 +50,7 @@ ABI_SYMBOLS = [
     "pcf_extract_hq", "pcf_clear", "pcf_dump_state", "pcf_get_stats", "pcf_reset_stats", "pcf_last_timings", "pcf_stream",
     "pcf_grid_buffer", "pcf_viewpoint_table", "pcf_log_compact", "pcf_log_replace", "pcf_set_slab", "pcf_plane_counts", "pcf_plane_point_counts", "pcf_exchange_counts", "pcf_exchange_scatter", "pcf_recv_buffer", "pcf_ipc_export", "pcf_ipc_open",
     "pcf_ipc_close_all", "pcf_install_records", "pcf_get_viewpoints", "pcf_set_viewpoints", "pcf_enable_peer_access", "pcf_kat_transform_voxel",
-    "pcf_kat_normal", "pcf_kat_score", "pcf_kat_format_float",
+    "pcf_kat_normal", "pcf_kat_score", "pcf_kat_format_float", "pcf_kat_clip_pack",
 ]
 
 _lib = None
@@ -120,6 +120,7 @@ def load_library():
     lib.pcf_enable_peer_access.argtypes = [vp, C.c_int32]
     lib.pcf_kat_transform_voxel.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
     lib.pcf_kat_format_float.argtypes = [C.c_float, C.c_int, C.c_char_p]
+    lib.pcf_kat_clip_pack.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_float, C.c_float, C.c_int32, vp, C.POINTER(C.c_uint32)]
     lib.pcf_kat_normal.argtypes = [vp, vp, C.c_uint32, vp]
     lib.pcf_kat_score.argtypes = [vp, vp, C.c_uint32, vp, vp, vp, vp, vp, vp, vp]
     _lib = lib
@@ -172,6 +173,18 @@ def _ptr(a):
     if isinstance(a, np.ndarray):
         return a.ctypes.data
     return a.data_ptr()   # torch tensor
+
+
+def kat_clip_pack(data, rows, cols, point_step, row_step, x_offset, lo, hi, isa=-1):
+    """The staging pool's clip-and-pack on a raw message buffer (host only: works without a GPU).  Returns (xyz [m, 3], isa used)."""
+    lib = load_library()
+    data = np.ascontiguousarray(data, np.uint8)
+    out = np.empty(3 * rows * cols + 16, np.float32)
+    m = C.c_uint32()
+    used = lib.pcf_kat_clip_pack(data.ctypes.data, rows, cols, point_step, row_step, x_offset, lo, hi, isa, out.ctypes.data, C.byref(m))
+    if used < 0:
+        raise PcfError(used, "pcf_kat_clip_pack: bad layout")
+    return out[:3 * m.value].reshape(-1, 3).copy(), used
 
 
 class Fusion:

@@ -32,27 +32,12 @@ struct StageJob {
     uint32_t frame_idx = 0;
 };
 
-// Order-preserving clip-and-pack of one cloud.  `out` must hold 3 * (rows * cols + 4) floats.  Returns the number of
-// packed points, padded with NaN points (which fail the kernel's clip) to a multiple of 4 so that every 256-point
-// chunk of the packed cloud is a 16-byte multiple for the bulk-copy kernel.
-inline uint32_t clip_pack(const StageJob& j, float clip_lo, float clip_hi, float* out) {
-    uint32_t k = 0;
-    for (uint32_t r = 0; r < j.rows; r++) {
-        const uint8_t* p = j.data + (size_t)r * j.row_step + j.x_offset;
-        const uint32_t step = j.point_step;
-        for (uint32_t c = 0; c < j.cols; c++, p += step) {
-            float v[3];
-            std::memcpy(v, p, 12);
-            out[3 * (size_t)k] = v[0];
-            out[3 * (size_t)k + 1] = v[1];
-            out[3 * (size_t)k + 2] = v[2];
-            k += (v[2] > clip_lo && v[2] < clip_hi) ? 1u : 0u;       // node.cpp:251; NaN fails
-        }
-    }
-    const float nan = std::numeric_limits<float>::quiet_NaN();
-    while (k & 3u) { out[3 * (size_t)k] = 0.f; out[3 * (size_t)k + 1] = 0.f; out[3 * (size_t)k + 2] = nan; k++; }
-    return k;
-}
+// Order-preserving clip-and-pack of one cloud (pcf_pack.cpp: AVX-512 / AVX2 / scalar, selected at run time).  `out` must
+// hold 3 * (rows * cols) + 16 floats.  Returns the number of packed points, padded with NaN points (which fail the kernel's
+// clip) to a multiple of 4 so that every 256-point chunk of the packed cloud is a 16-byte multiple for the bulk-copy kernel.
+uint32_t clip_pack(const StageJob& j, float clip_lo, float clip_hi, float* out);
+int clip_pack_isa();     // 0 scalar, 1 AVX2, 2 AVX-512
+uint32_t clip_pack_with(int isa, const StageJob& j, float clip_lo, float clip_hi, float* out);   // tests: force an implementation
 
 class Stager {
    public:
@@ -144,7 +129,7 @@ class Stager {
             const int s = (int)(seq % slots_.size());
             hooks_.slot_wait(s);
             Slot& sl = slots_[s];
-            const size_t need = 3 * ((size_t)j.rows * j.cols + 4);
+            const size_t need = 3 * (size_t)j.rows * j.cols + 16;
             if (need > sl.cap) {
                 if (sl.p) hooks_.free_pinned(sl.p);
                 sl.cap = need + need / 8;

@@ -95,7 +95,7 @@ struct pcf_ctx {
     // scratch
     DevBuf scan1, scan2, tmpA, tmpB, tmpC, tmpD, hist, sort_tab, keysA, keysB, valsA, valsB, sorted, uv_cell, uv_off, nidx,
         sc_a, sc_b, sc_c, flags, slots, cand, res_dev, total_dev, sc_keys, sc_ids, sc_order, sc_okeys, sc_tab;
-    int score_unroll = 2;                 // PCF_SCORE_UNR: cylinder tests evaluated back to back in k_score (1, 2 or 4)
+    int score_unroll = 1;                 // PCF_SCORE_UNR: cylinder tests evaluated back to back in k_score (1, 2 or 4; measured: no gain)
     bool score_balance = true;            // PCF_SCORE_BALANCE=0 keeps the x-major voxel -> lane assignment
     uint32_t* total_host = nullptr;       // pinned, 4 words
     // host results (pinned)
@@ -1470,6 +1470,17 @@ int pcf_kat_transform_voxel(pcf_ctx* c, const float* pts_host, uint32_t n, uint3
     CU(cudaStreamSynchronize(c->stream));
     cudaFree(d_in); cudaFree(d_w); cudaFree(d_ijk); cudaFree(d_k);
     return PCF_OK;
+}
+// the staging pool's clip-and-pack on its own (host code, no context and no GPU needed): `isa` 0 scalar, 1 AVX2, 2 AVX-512,
+// -1 the one the pool uses on this CPU.  Returns the implementation that ran, or a negative status.
+int pcf_kat_clip_pack(const uint8_t* data, uint32_t rows, uint32_t cols, uint32_t point_step, uint64_t row_step, uint32_t x_offset,
+                      float clip_lo, float clip_hi, int32_t isa, float* out_xyz, uint32_t* n_out) {
+    if (!data || !out_xyz || !n_out || point_step % 4 || x_offset % 4 || point_step < x_offset + 12) return PCF_ERR_INVALID;
+    StageJob j;
+    j.data = data; j.rows = rows; j.cols = cols; j.row_step = row_step; j.point_step = point_step; j.x_offset = x_offset;
+    const int use = isa < 0 ? clip_pack_isa() : std::min<int>(isa, clip_pack_isa());
+    *n_out = clip_pack_with(use, j, clip_lo, clip_hi, out_xyz);
+    return use;
 }
 int pcf_kat_normal(pcf_ctx* c, const float* xyz_host, uint32_t n_points, float* normal3) {
     if (!c || !xyz_host || !normal3) return PCF_ERR_INVALID;

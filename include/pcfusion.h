@@ -241,6 +241,10 @@ int pcf_enable_peer_access(pcf_ctx* ctx, int32_t peer_device);
 /* ---- known-answer hooks: run ONE device function over an array (tests bit-compare with the oracle) ---- */
 int pcf_kat_transform_voxel(pcf_ctx* ctx, const float* pts_host, uint32_t n, uint32_t stride_floats,
                             const double pose[16], float* world_xyz, int32_t* ijk, uint8_t* kept);
+/* clip-and-pack of the staging pool (host code; runs without a context or a GPU).  isa: 0 scalar, 1 AVX2, 2 AVX-512, -1 = what
+ * the pool uses on this CPU; out_xyz needs 3 * rows * cols + 16 floats.  Returns the implementation that ran (>= 0). */
+int pcf_kat_clip_pack(const uint8_t* data, uint32_t rows, uint32_t cols, uint32_t point_step, uint64_t row_step, uint32_t x_offset,
+                      float clip_lo, float clip_hi, int32_t isa, float* out_xyz, uint32_t* n_out);
 int pcf_kat_normal(pcf_ctx* ctx, const float* xyz_host, uint32_t n_points, float* normal3);
 int pcf_kat_format_float(float v, int precision, char* out32);   /* the writer's float formatting (6 = CSV %g, 8 = PCD %.8g) */
 int pcf_kat_score(pcf_ctx* ctx, const float* xyz_host, uint32_t n_points, const float axis_pt[3],

@@ -55,7 +55,8 @@ def test_stage_frame_then_push_equals_plain_push(pcf, small):
         a.push_frame(pts, T, i)
         staged, m = b.stage_frame(pts)
         assert m % 4 == 0 and m <= len(pts) + 3
-        inside = (pts[:, 2] > np.float32(0.28)) & (pts[:, 2] < np.float32(0.6))
+        z = pts[:, 2].astype(np.float64)             # node.cpp:251 compares the float promoted to double
+        inside = (z > 0.28) & (z < 0.6)
         assert m - int(inside.sum()) in (0, 1, 2, 3)
         assert np.array_equal(staged[:int(inside.sum())].view(np.uint32), pts[inside][:, :3].view(np.uint32))   # order kept
         b.push_frame(np.ascontiguousarray(staged), T, i)
