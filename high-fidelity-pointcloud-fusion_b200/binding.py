@@ -25,7 +25,7 @@ class _Config(C.Structure):
     _fields_ = [("box", C.c_double * 6), ("res", C.c_float * 3), ("clip_zmin", C.c_double), ("clip_zmax", C.c_double),
                 ("k_neighbourhood", C.c_int32), ("walk_k", C.c_int32), ("min_neighbours", C.c_int32),
                 ("cylinder_radius", C.c_double), ("ball_radius", C.c_double), ("device", C.c_int32),
-                ("max_frames", C.c_uint32), ("log_capacity_hint", C.c_uint64), ("stage_threads", C.c_int32)]
+                ("max_frames", C.c_uint32), ("log_capacity_hint", C.c_uint64), ("stage_threads", C.c_int32), ("stage_raw_lanes", C.c_int32)]
 
 
 class _Result(C.Structure):
@@ -191,7 +191,7 @@ class Fusion:
     """One fusion context on one GPU (= the reference's PointcloudFusion + OccupancyGrid pair)."""
 
     def __init__(self, box, res, clip_zmin=0.28, clip_zmax=0.6, device=0, max_frames=1 << 16, log_capacity_hint=0,
-                 walk_k=3, min_neighbours=20, started=True, stage_threads=0):
+                 walk_k=3, min_neighbours=20, started=True, stage_threads=0, stage_raw_lanes=0):
         self.lib = load_library()
         cfg = _Config()
         self.lib.pcf_default_config(C.byref(cfg))
@@ -201,7 +201,7 @@ class Fusion:
         cfg.clip_zmin, cfg.clip_zmax = clip_zmin, clip_zmax
         cfg.device, cfg.max_frames, cfg.log_capacity_hint = device, max_frames, log_capacity_hint
         cfg.walk_k, cfg.min_neighbours = walk_k, min_neighbours
-        cfg.stage_threads = stage_threads
+        cfg.stage_threads, cfg.stage_raw_lanes = stage_threads, stage_raw_lanes
         h = C.c_void_p()
         rc = self.lib.pcf_create(C.byref(cfg), C.byref(h))
         if rc != 0:

@@ -40,6 +40,7 @@ struct GridParams {
     int32_t walk_k;
     int32_t min_neighbours;
     float ball_radius_f;    // float(kBballRadius), OG.hpp:42
+    float cylinder_thr;     // float threshold equivalent to the double compare of OG.hpp:262:  (double)d < radius  <=>  d < cylinder_thr
     double cylinder_radius; // OG.hpp:36
 };
 
@@ -256,9 +257,10 @@ PCF_HD float score_test(const Axis& ax, V3 pt, V3& proj) {
     V3 diff = pt - proj;
     return sqrtf(sqnorm(diff));
 }
-PCF_HD void score_fold(const GridParams& g, Stats& s, V3 proj, float dist_f) {
+// fold of one IN-CYLINDER point (OG.hpp:264-273 / 428-438)
+PCF_HD void score_apply(Stats& s, V3 proj, float dist_f) {
     double dist = (double)dist_f;
-    if (dist < g.cylinder_radius) {
+    {
         s.count++;
         V3 old_mean = s.centroid;
         float c = (float)s.count;
@@ -272,6 +274,9 @@ PCF_HD void score_fold(const GridParams& g, Stats& s, V3 proj, float dist_f) {
         s.sd_dist = (float)((double)s.sd_dist +
                             ((dist - (double)s.mean_dist) * (dist - (double)old_md) - (double)s.sd_dist) / dc);
     }
+}
+PCF_HD void score_fold(const GridParams& g, Stats& s, V3 proj, float dist_f) {
+    if ((double)dist_f < g.cylinder_radius) score_apply(s, proj, dist_f);      // OG.hpp:262 / 426
 }
 PCF_HD void score_point(const GridParams& g, const Axis& ax, Stats& s, V3 pt) {
     V3 proj;

@@ -9,6 +9,12 @@
 // arrival order every per-voxel buffer depends on (OG.hpp:211,230,239) is unchanged; the kernel still applies the
 // FP64 transform, the box test and (again, harmlessly) the clip.  What crosses PCIe is the clipped cloud
 // (C2: 5.5 instead of 16 bytes per input point), which is what bounds the end-to-end rate.
+//
+// Raw lanes.  Packing is bound by the host's memory bandwidth and cores, the unstaged upload by PCIe: while the packers
+// are saturated the link is half idle.  A few extra "raw lane" threads take clouds from the same queue and upload them
+// as they are (pinned float4 / packed-xyz arrays only; anything else they pack like everybody else).  A raw lane waits for
+// its own copy to finish before it takes the next cloud, so it only ever uses link time the staged copies leave free, and
+// the same in-order hand-over keeps the arrival order.  Results are identical either way: the kernel applies the clip.
 #pragma once
 #include <condition_variable>
 #include <cstdint>
@@ -48,14 +54,21 @@ class Stager {
         std::function<void(int)> slot_wait;                         // block until the last upload out of slot s has completed
         // hand a staged cloud to the GPU (H2D copy + integration launch); called in submission order, one at a time
         std::function<int(int slot, const float* xyz, uint32_t n_staged, uint32_t n_offered, const double* pose, uint32_t frame_idx)> push;
+        // raw lanes: can this cloud be uploaded as it is (pinned, plain [n, stride] array)?  upload it from the caller's
+        // memory (in submission order, like push); block until lane `lane`'s last upload has left the caller's buffer
+        std::function<bool(const StageJob&)> raw_ok;
+        std::function<int(int lane, const StageJob&)> push_raw;
+        std::function<void(int lane)> raw_wait;
     };
 
-    Stager(int threads, float clip_lo, float clip_hi, Hooks hooks)
+    Stager(int threads, int raw_lanes, float clip_lo, float clip_hi, Hooks hooks)
         : clip_lo_(clip_lo), clip_hi_(clip_hi), hooks_(std::move(hooks)) {
         n_threads_ = threads < 1 ? 1 : threads;
-        slots_.resize((size_t)n_threads_ * 2);
+        n_raw_ = raw_lanes < 0 ? 0 : raw_lanes;
+        slots_.resize((size_t)(n_threads_ + n_raw_) * 2);
         max_queue_ = (size_t)n_threads_ * 4;
-        for (int t = 0; t < n_threads_; t++) pool_.emplace_back(&Stager::worker, this);
+        for (int t = 0; t < n_threads_; t++) pool_.emplace_back(&Stager::worker, this, -1);
+        for (int t = 0; t < n_raw_; t++) pool_.emplace_back(&Stager::worker, this, t);
     }
     ~Stager() {
         drain();
@@ -64,19 +77,27 @@ class Stager {
             quit_ = true;
         }
         cv_work_.notify_all();
+        cv_raw_.notify_all();
         cv_order_.notify_all();
         for (std::thread& t : pool_) t.join();
         for (Slot& s : slots_) if (s.p) hooks_.free_pinned(s.p);
     }
     int n_slots() const { return (int)slots_.size(); }
     int n_threads() const { return n_threads_; }
+    int n_raw_lanes() const { return n_raw_; }
+    uint64_t raw_pushed() {
+        std::lock_guard<std::mutex> lk(m_);
+        return raw_pushed_;
+    }
 
     void submit(const StageJob& j) {                                 // node.cpp:345-347 (clouds_.push_back)
         std::unique_lock<std::mutex> lk(m_);
         cv_space_.wait(lk, [&] { return queue_.size() < max_queue_; });
         queue_.push_back(j);
+        const bool backlog = n_raw_ > 0 && queue_.size() >= (size_t)n_threads_;
         lk.unlock();
         cv_work_.notify_one();
+        if (backlog) cv_raw_.notify_one();       // clouds are piling up behind the packers: a raw lane may help
     }
     // node.cpp:356: drop what no worker has taken yet.  Returns the number of dropped clouds.
     size_t drop_queued() {
@@ -109,19 +130,34 @@ class Stager {
    private:
     struct Slot { float* p = nullptr; size_t cap = 0; };
 
-    void worker() {
+    // raw_lane < 0: packer.  raw_lane >= 0: raw lane (uploads eligible clouds unstaged, packs the others)
+    void worker(int raw_lane) {
         if (hooks_.thread_init) hooks_.thread_init(0);
         for (;;) {
             StageJob j;
             uint64_t seq;
+            if (raw_lane >= 0) hooks_.raw_wait(raw_lane);            // the link is free of this lane's previous cloud
             {
                 std::unique_lock<std::mutex> lk(m_);
-                cv_work_.wait(lk, [&] { return quit_ || !queue_.empty(); });
-                if (queue_.empty()) return;                          // quit
+                // a raw lane only helps out when clouds are piling up behind the packers
+                if (raw_lane < 0) cv_work_.wait(lk, [&] { return quit_ || !queue_.empty(); });
+                else cv_raw_.wait(lk, [&] { return quit_ || queue_.size() >= (size_t)n_threads_; });
+                if (quit_ && queue_.empty()) return;
+                if (queue_.empty()) continue;
                 j = queue_.front();
                 queue_.pop_front();
                 seq = next_seq_++;                                   // taken in FIFO order under the lock: seq order == submission order
                 cv_space_.notify_one();
+                if (raw_lane >= 0 && hooks_.raw_ok(j)) {
+                    cv_order_.wait(lk, [&] { return next_push_ == seq; });
+                    int rc = hooks_.push_raw(raw_lane, j);
+                    if (rc < 0 && err_ == 0) err_ = rc;
+                    next_push_++;
+                    raw_pushed_++;
+                    lk.unlock();
+                    cv_order_.notify_all();
+                    continue;
+                }
                 // the slot was last used by cloud seq - n_slots: that one must have been handed over before it is refilled
                 const uint64_t ns = slots_.size();
                 cv_order_.wait(lk, [&] { return seq < ns || next_push_ > seq - ns; });
@@ -150,13 +186,14 @@ class Stager {
 
     float clip_lo_, clip_hi_;
     Hooks hooks_;
-    int n_threads_ = 1;
+    int n_threads_ = 1, n_raw_ = 0;
+    uint64_t raw_pushed_ = 0;
     std::vector<Slot> slots_;
     std::vector<std::thread> pool_;
     std::deque<StageJob> queue_;
     size_t max_queue_ = 8;
     std::mutex m_;
-    std::condition_variable cv_work_, cv_space_, cv_order_;
+    std::condition_variable cv_work_, cv_raw_, cv_space_, cv_order_;
     uint64_t next_seq_ = 0, next_push_ = 0;
     int err_ = 0;
     bool quit_ = false;

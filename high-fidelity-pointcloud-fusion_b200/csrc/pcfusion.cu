@@ -90,6 +90,8 @@ struct pcf_ctx {
     // host staging pool (pcf_submit_*): clip-and-pack threads + pinned slots, see pcf_stager.hpp
     std::unique_ptr<pcf::Stager> stager;
     std::vector<cudaEvent_t> slot_ev;     // per pinned slot: its last upload has left the slot
+    std::vector<cudaEvent_t> raw_ev;      // per raw lane: its last unstaged upload has left the caller's buffer
+    uint64_t raw_seen = 0;                // raw uploads already waited for by a drain
     uint64_t staged_dropped = 0;          // clouds dropped by pcf_reset before a staging thread took them
 
     // scratch
@@ -97,6 +99,7 @@ struct pcf_ctx {
         sc_a, sc_b, sc_c, flags, slots, cand, res_dev, total_dev, sc_keys, sc_ids, sc_order, sc_okeys, sc_tab;
     int score_unroll = 1;                 // PCF_SCORE_UNR: cylinder tests evaluated back to back in k_score (1, 2 or 4; measured: no gain)
     bool score_balance = true;            // PCF_SCORE_BALANCE=0 keeps the x-major voxel -> lane assignment
+    int score_coop = -1;                  // PCF_SCORE_COOP: 1 always / 0 never use k_score_coop on canonical schedules (-1: by point density)
     uint32_t* total_host = nullptr;       // pinned, 4 words
     // host results (pinned)
     void* res_host = nullptr;
@@ -222,6 +225,7 @@ int build_grid_params(pcf_ctx* c) {
     g.min_neighbours = cfg.min_neighbours;
     g.ball_radius_f = (float)cfg.ball_radius;
     g.cylinder_radius = cfg.cylinder_radius;
+    g.cylinder_thr = thr_hi(cfg.cylinder_radius);     // smallest float f with double(f) >= radius
     return PCF_OK;
 }
 
@@ -517,7 +521,13 @@ int run_scoring(pcf_ctx* c) {
 #define SCORE_ARGS order, (const uint32_t*)c->n_cell.p, (const float4*)c->n_nrm.p, (const uint32_t*)c->n_mark.p, nn, c->g, c->occ_bits, c->occ_rank, \
                    (const uint32_t*)c->uv_off.p, (const uint32_t*)c->nidx.p, (const float4*)c->sorted.p, (const uint32_t*)c->holder, so,  \
                    (uint32_t)c->n_points, (const uint32_t*)c->uv_cell.p, fault
-    if (!simple) LAUNCH(c, (k_score<false, 1>), div_up(nn, 128), 128, SCORE_ARGS);
+    // dense buffers (the scans of real surfaces): cooperative kernel; a handful of points per voxel (C5's synthetic sheets):
+    // one thread per voxel wastes less
+    const bool coop = simple && c->score_coop != 0 && (c->score_coop > 0 || c->n_points >= 8ull * std::max<uint32_t>(c->n_vox, 1u));
+    if (coop) LAUNCH(c, k_score_coop, div_up(nn, kCoopWarps * 32), kCoopWarps * 32, order, (const uint32_t*)c->n_cell.p, (const float4*)c->n_nrm.p, nn, c->g,
+                     c->occ_bits, c->occ_rank, (const uint32_t*)c->uv_off.p, (const float4*)c->sorted.p, so, (uint32_t)c->n_points,
+                     (const uint32_t*)c->uv_cell.p, fault);
+    else if (!simple) LAUNCH(c, (k_score<false, 1>), div_up(nn, 128), 128, SCORE_ARGS);
     else if (c->score_unroll >= 4) LAUNCH(c, (k_score<true, 4>), div_up(nn, 128), 128, SCORE_ARGS);
     else if (c->score_unroll >= 2) LAUNCH(c, (k_score<true, 2>), div_up(nn, 128), 128, SCORE_ARGS);
     else LAUNCH(c, (k_score<true, 1>), div_up(nn, 128), 128, SCORE_ARGS);
@@ -602,6 +612,7 @@ void destroy_impl(pcf_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stager) { c->stager->drain(); c->stager.reset(); }      // joins the staging threads, frees the pinned slots
     for (cudaEvent_t e : c->slot_ev) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->raw_ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     DevBuf* bufs[] = {&c->n_cell, &c->n_nrm, &c->n_mark, &c->scan1, &c->scan2, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->hist, &c->sort_tab,
@@ -656,6 +667,11 @@ int drain_staged(pcf_ctx* c) {
     if (!c->stager) return PCF_OK;
     int rc = c->stager->drain();
     if (rc < 0 && c->err.empty()) c->err = "a staged frame failed to integrate";
+    const uint64_t raw = c->stager->raw_pushed();
+    if (raw != c->raw_seen) {            // clouds uploaded unstaged are read by the copy engine until their copy completes
+        cudaStreamSynchronize(c->copy_stream);
+        c->raw_seen = raw;
+    }
     return rc < 0 ? rc : PCF_OK;
 }
 #define ENTER(c)                                  \
@@ -687,6 +703,7 @@ void pcf_default_config(pcf_config* cfg) {
     cfg->max_frames = 1u << 16;
     cfg->log_capacity_hint = 0;
     cfg->stage_threads = 0;                                   // auto
+    cfg->stage_raw_lanes = 0;                                 // default (2)
 }
 
 int pcf_create(const pcf_config* cfg, pcf_ctx** out) {
@@ -723,6 +740,8 @@ int pcf_create(const pcf_config* cfg, pcf_ctx** out) {
         if (u && atoi(u) > 0) c->score_unroll = atoi(u);
         const char* bl = getenv("PCF_SCORE_BALANCE");
         if (bl) c->score_balance = atoi(bl) != 0;
+        const char* co = getenv("PCF_SCORE_COOP");
+        if (co) c->score_coop = atoi(co) != 0 ? 1 : 0;
     }
     CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -891,9 +910,26 @@ static int ensure_stager(pcf_ctx* c) {
     h.push = [c](int s, const float* xyz, uint32_t n_staged, uint32_t n_offered, const double* pose, uint32_t frame_idx) {
         return push_host_cloud_impl(c, xyz, (size_t)n_staged * 12, 0, n_staged, 3, nullptr, pose, nullptr, frame_idx, n_offered, c->slot_ev[s]);
     };
-    c->slot_ev.assign((size_t)threads * 2, nullptr);
+    int raw_lanes = c->cfg.stage_raw_lanes == 0 ? 2 : std::max(c->cfg.stage_raw_lanes, 0);
+    if (const char* e = getenv("PCF_RAW_LANES")) raw_lanes = std::max(atoi(e), 0);
+    h.raw_ok = [](const StageJob& j) {
+        if (j.x_offset != 0 || (j.point_step != 16 && j.point_step != 12) || ((uintptr_t)j.data & 15u)) return false;
+        if (j.rows > 1 && j.row_step != (uint64_t)j.cols * j.point_step) return false;
+        if (j.point_step == 12 && ((uint64_t)j.rows * j.cols) % 4) return false;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, j.data) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;                   // page-locked: the copy engine can read it asynchronously
+    };
+    h.push_raw = [c](int lane, const StageJob& j) {
+        const uint32_t n = j.rows * j.cols;
+        return push_host_cloud_impl(c, j.data, (size_t)n * j.point_step, 0, n, j.point_step / 4, nullptr, j.pose, nullptr, j.frame_idx, n, c->raw_ev[lane]);
+    };
+    h.raw_wait = [c](int lane) { cudaEventSynchronize(c->raw_ev[lane]); };
+    c->slot_ev.assign((size_t)(threads + raw_lanes) * 2, nullptr);
     for (cudaEvent_t& e : c->slot_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    c->stager.reset(new Stager(threads, c->g.clip_lo, c->g.clip_hi, std::move(h)));
+    c->raw_ev.assign((size_t)raw_lanes, nullptr);
+    for (cudaEvent_t& e : c->raw_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->stager.reset(new Stager(threads, raw_lanes, c->g.clip_lo, c->g.clip_hi, std::move(h)));
     return PCF_OK;
 }
 
@@ -939,7 +975,11 @@ int pcf_staged_count(pcf_ctx* c, uint64_t* n) {
 }
 int pcf_wait_staged(pcf_ctx* c, uint64_t n) {
     if (!c) return PCF_ERR_INVALID;
-    if (c->stager) c->stager->wait_staged(n);
+    if (c->stager) {
+        c->stager->wait_staged(n);
+        const uint64_t raw = c->stager->raw_pushed();
+        if (raw != c->raw_seen) { CU(cudaSetDevice(c->device)); CU(cudaStreamSynchronize(c->copy_stream)); c->raw_seen = raw; }
+    }
     return PCF_OK;
 }
 

@@ -57,6 +57,9 @@ typedef struct {
     uint64_t log_capacity_hint;  /* initial point-log capacity in INPUT points; grows on demand */
     int32_t stage_threads;       /* host staging threads of pcf_submit_* (the reference has ONE addPoints thread,
                                     node.cpp:166,218); 0 = min(16, hardware threads); env PCF_STAGE_THREADS overrides */
+    int32_t stage_raw_lanes;     /* extra threads that upload pinned float4 / xyz clouds UNSTAGED while clouds pile up behind the
+                                    packers, using the PCIe time the staged copies leave free; 0 = default (2), < 0 = none;
+                                    env PCF_RAW_LANES overrides */
 } pcf_config;
 
 /* Extraction output, structure of arrays, x-major voxel order = the reference's scan order

@@ -19,18 +19,25 @@ def small(pcf):
     return importlib.import_module(pcf.__name__ + ".synth").small_sphere(6)
 
 
-@pytest.mark.parametrize("threads", [1, 5])
+@pytest.mark.parametrize("threads,raw_lanes,pinned", [(1, -1, False), (5, -1, False), (1, 2, True), (3, 1, True), (2, 0, False)])
 @pytest.mark.parametrize("update_every", [None, 2])
-def test_submit_frame_bit_identical_to_push_frame_and_oracle(pcf, oracle, small, threads, update_every):
+def test_submit_frame_bit_identical_to_push_frame_and_oracle(pcf, oracle, small, threads, raw_lanes, pinned, update_every):
+    """raw_lanes: -1 none; 2 / 1 with pinned clouds: some clouds are uploaded unstaged by the raw lanes while the packers are
+    busy (which ones depends on timing -- the grid must not); pageable clouds are always packed."""
+    import torch
     g = small.grid
-    a = pcf.Fusion(g.box, g.res, stage_threads=threads)
+    a = pcf.Fusion(g.box, g.res, stage_threads=threads, stage_raw_lanes=raw_lanes)
     og = oracle.OracleGrid(g.box, g.res)
     keep = []
-    for rep in range(3):                       # 18 frames: more clouds than pinned slots (2 x threads), the ring wraps
+    for rep in range(3):                       # 18 frames: more clouds than pinned slots, the ring wraps
         for i in range(small.n_frames):
             pts, T = small.frame(i)
             k = rep * small.n_frames + i
             pose = np.ascontiguousarray(T, np.float64).reshape(16)
+            if pinned:
+                pts_t = torch.from_numpy(pts).pin_memory()
+                pts = pts_t.numpy()
+                keep.append(pts_t)
             keep.append((pts, pose))           # submitted clouds are read asynchronously
             assert a.submit_frame(pts, pose, k) == 0
             og.add_frame(pts, T)
@@ -39,7 +46,8 @@ def test_submit_frame_bit_identical_to_push_frame_and_oracle(pcf, oracle, small,
     a.update(); og.update()
     st = a.stats()
     assert st["frames_pushed"] == 18 and st["points_offered"] == 18 * small.points_per_frame
-    assert st["h2d_bytes"] < 18 * small.points_per_frame * 12      # only the clipped cloud crossed PCIe
+    if raw_lanes < 0 or not pinned:
+        assert st["h2d_bytes"] < 18 * small.points_per_frame * 12  # only the clipped cloud crossed PCIe
     assert_result_parity(a.extract(), og.download(), "submit_frame result.")
     assert_same(a.state(), og.state(), STATE_FIELDS, "submit_frame state.")
     a.close()
@@ -136,13 +144,14 @@ def test_scoring_variants_are_bit_identical(pcf, oracle, small):
     want = og.download()
     assert len(want) > 20000
     try:
-        for unr, bal in [(1, 0), (1, 1), (2, 1), (4, 1), (4, 0)]:
-            os.environ["PCF_SCORE_UNR"], os.environ["PCF_SCORE_BALANCE"] = str(unr), str(bal)
+        for unr, bal, coop in [(1, 0, 0), (1, 1, 0), (2, 1, 0), (4, 1, 0), (4, 0, 0), (1, 1, 1), (1, 0, 1)]:
+            os.environ["PCF_SCORE_UNR"], os.environ["PCF_SCORE_BALANCE"], os.environ["PCF_SCORE_COOP"] = str(unr), str(bal), str(coop)
             f = pcf.Fusion(g.box, g.res)
             for i, (pts, T) in enumerate(frames):
                 f.push_frame(pts, T, i)
             f.update()
-            assert_result_parity(f.extract(), want, f"k_score unroll={unr} balance={bal}: ")
+            assert_result_parity(f.extract(), want, f"k_score unroll={unr} balance={bal} coop={coop}: ")
             f.close()
     finally:
-        os.environ.pop("PCF_SCORE_UNR", None); os.environ.pop("PCF_SCORE_BALANCE", None)
+        for k in ("PCF_SCORE_UNR", "PCF_SCORE_BALANCE", "PCF_SCORE_COOP"):
+            os.environ.pop(k, None)
