@@ -50,7 +50,7 @@ ABI_SYMBOLS = [
     "pcf_extract_hq", "pcf_clear", "pcf_dump_state", "pcf_get_stats", "pcf_reset_stats", "pcf_last_timings", "pcf_stream",
     "pcf_grid_buffer", "pcf_viewpoint_table", "pcf_log_compact", "pcf_log_replace", "pcf_set_slab", "pcf_plane_counts", "pcf_plane_point_counts", "pcf_exchange_counts", "pcf_exchange_scatter", "pcf_recv_buffer", "pcf_ipc_export", "pcf_ipc_open",
     "pcf_ipc_close_all", "pcf_install_records", "pcf_get_viewpoints", "pcf_set_viewpoints", "pcf_enable_peer_access", "pcf_kat_transform_voxel",
-    "pcf_kat_normal", "pcf_kat_score", "pcf_kat_format_float", "pcf_kat_clip_pack",
+    "pcf_kat_normal", "pcf_kat_score", "pcf_kat_format_float", "pcf_kat_clip_pack", "pcf_kat_div",
 ]
 
 _lib = None
@@ -122,6 +122,7 @@ def load_library():
     lib.pcf_kat_format_float.argtypes = [C.c_float, C.c_int, C.c_char_p]
     lib.pcf_kat_clip_pack.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_float, C.c_float, C.c_int32, vp, C.POINTER(C.c_uint32)]
     lib.pcf_kat_normal.argtypes = [vp, vp, C.c_uint32, vp]
+    lib.pcf_kat_div.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.pcf_kat_score.argtypes = [vp, vp, C.c_uint32, vp, vp, vp, vp, vp, vp, vp]
     _lib = lib
     return lib
@@ -413,6 +414,13 @@ class Fusion:
         self._ck(self.lib.pcf_kat_transform_voxel(self.h, pts.ctypes.data, n, stride, pose.ctypes.data, w.ctypes.data,
                                                   ijk.ctypes.data, kept.ctypes.data))
         return w, ijk, kept
+
+    def kat_div(self, x, c):
+        """(mismatches, index of one) of the scoring kernel's shared-reciprocal division vs x / c on the device."""
+        x, c = np.ascontiguousarray(x, np.float32), np.ascontiguousarray(c, np.float32)
+        m, bad = C.c_uint32(), C.c_uint32()
+        self._ck(self.lib.pcf_kat_div(self.h, x.ctypes.data, c.ctypes.data, len(x), C.byref(m), C.byref(bad)))
+        return int(m.value), int(bad.value)
 
     def kat_normal(self, xyz):
         xyz = np.ascontiguousarray(xyz, np.float32)

@@ -1522,6 +1522,26 @@ int pcf_kat_clip_pack(const uint8_t* data, uint32_t rows, uint32_t cols, uint32_
     *n_out = clip_pack_with(use, j, clip_lo, clip_hi, out_xyz);
     return use;
 }
+// x[i] / c[i] through the scoring kernel's shared-reciprocal division vs the compiler's div.rn.f32: number of results that
+// differ in any bit (two NaNs count as equal) and the index of one of them
+int pcf_kat_div(pcf_ctx* c, const float* x_host, const float* c_host, uint32_t n, uint32_t* mismatches, uint32_t* first_bad) {
+    if (!c || !x_host || !c_host || !mismatches || !first_bad) return PCF_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    float *dx, *dc; uint32_t* dm;
+    CU(cudaMalloc(&dx, (size_t)n * 4 + 4));
+    CU(cudaMalloc(&dc, (size_t)n * 4 + 4));
+    CU(cudaMalloc(&dm, 8));
+    CU(cudaMemsetAsync(dm, 0, 8, c->stream));
+    CU(cudaMemcpyAsync(dx, x_host, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(dc, c_host, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    if (n) LAUNCH(c, k_kat_div, div_up(n, 256), 256, dx, dc, n, dm, dm + 1);
+    uint32_t h[2];
+    CU(cudaMemcpyAsync(h, dm, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *mismatches = h[0]; *first_bad = h[1];
+    cudaFree(dx); cudaFree(dc); cudaFree(dm);
+    return PCF_OK;
+}
 int pcf_kat_normal(pcf_ctx* c, const float* xyz_host, uint32_t n_points, float* normal3) {
     if (!c || !xyz_host || !normal3) return PCF_ERR_INVALID;
     CU(cudaSetDevice(c->device));

@@ -248,6 +248,8 @@ int pcf_kat_transform_voxel(pcf_ctx* ctx, const float* pts_host, uint32_t n, uin
  * the pool uses on this CPU; out_xyz needs 3 * rows * cols + 16 floats.  Returns the implementation that ran (>= 0). */
 int pcf_kat_clip_pack(const uint8_t* data, uint32_t rows, uint32_t cols, uint32_t point_step, uint64_t row_step, uint32_t x_offset,
                       float clip_lo, float clip_hi, int32_t isa, float* out_xyz, uint32_t* n_out);
+/* the cooperative scoring kernel's division (shared reciprocal of float(count)) against the compiler's IEEE division */
+int pcf_kat_div(pcf_ctx* ctx, const float* x_host, const float* c_host, uint32_t n, uint32_t* mismatches, uint32_t* first_bad);
 int pcf_kat_normal(pcf_ctx* ctx, const float* xyz_host, uint32_t n_points, float* normal3);
 int pcf_kat_format_float(float v, int precision, char* out32);   /* the writer's float formatting (6 = CSV %g, 8 = PCD %.8g) */
 int pcf_kat_score(pcf_ctx* ctx, const float* xyz_host, uint32_t n_points, const float axis_pt[3],

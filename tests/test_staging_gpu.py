@@ -155,3 +155,28 @@ def test_scoring_variants_are_bit_identical(pcf, oracle, small):
     finally:
         for k in ("PCF_SCORE_UNR", "PCF_SCORE_BALANCE", "PCF_SCORE_COOP"):
             os.environ.pop(k, None)
+
+
+def test_shared_reciprocal_division_is_the_ieee_division(pcf, small):
+    """k_score_coop divides six numbers by float(count) with ONE reciprocal (csrc/pcf_kernels.cuh div_shared): bit-identical to
+    x / c (the compiler's div.rn.f32) for every integer divisor up to 2^17, random ones up to 2^24, and dividends covering
+    every exponent, both zeros, denormals, infinities, NaNs and the magnitudes the fold really sees."""
+    f = pcf.Fusion(small.grid.box, small.grid.res)
+    rng = np.random.default_rng(11)
+    n_div = 1 << 17
+    for rep in range(6):
+        c = np.arange(1, n_div + 1, dtype=np.float32)
+        if rep >= 3:
+            c = rng.integers(1, 1 << 24, n_div).astype(np.float32)
+        if rep % 3 == 0:          # any bit pattern
+            x = rng.integers(0, 1 << 32, n_div, dtype=np.uint64).astype(np.uint32).view(np.float32)
+        elif rep % 3 == 1:        # the fold's magnitudes: coordinate differences and variance terms
+            x = (rng.standard_normal(n_div) * 10.0 ** rng.uniform(-12, 0, n_div)).astype(np.float32)
+        else:                     # quotients that land next to rounding boundaries: x = c * (k + 0.5 ulp-ish)
+            k = rng.integers(1, 1 << 23, n_div).astype(np.float64)
+            x = (c.astype(np.float64) * (k + rng.choice([0.5, 0.4999999, 0.5000001], n_div)) * 2.0 ** rng.integers(-60, 20, n_div)).astype(np.float32)
+        special = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 1e-38, 3e38, 2.0 ** -80, 2.0 ** 80, 2.0 ** -81], np.float32)
+        x[:len(special)] = special
+        m, bad = f.kat_div(x, c)
+        assert m == 0, f"rep {rep}: {m} quotients differ, e.g. x={x[bad]!r} c={c[bad]!r}"
+    f.close()
