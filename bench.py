@@ -128,7 +128,7 @@ def host_threads(world_local=1):
         n = len(os.sched_getaffinity(0))
     except Exception:
         n = os.cpu_count() or 4
-    return max(1, n), max(2, min(16, n // max(1, world_local)))
+    return max(1, n), max(2, min(16, (n // max(1, world_local)) * 3 // 4))
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -235,11 +235,11 @@ def multi_gpu_parity(pcf, sh, local, rank, world):
     detail = []
     for update_every in (0,):
         fus = pcf.Fusion(g.box, g.res, device=local)
-        peer = sh.PeerExchange(fus)
+        peer = sh.DeviceExchange(fus)
         lo, hi = sh.frame_block(scene.n_frames, rank, world)
         for i in range(lo, hi):
             fus.push_frame(*scene.frame(i), i)
-        _, full, _ = sh.merge_and_extract_v2(fus, peer=peer)
+        _, full, _ = sh.merge_and_extract_v3(fus, peer=peer, gather_to=0)
         if rank == 0:
             one = pcf.Fusion(g.box, g.res, device=local)
             for i in range(scene.n_frames):
@@ -295,7 +295,7 @@ def c3_strong(pcf, sh, local, rank, world, peer_factory):
         barrier()
         t0 = time.perf_counter()
         if world > 1:
-            _, _, tm = sh.merge_and_extract_v2(fus, peer=peer, gather_to=None)     # every rank keeps its own x-slab
+            _, _, tm = sh.merge_and_extract_v3(fus, peer=peer, gather_to=None)     # every rank keeps its own x-slab
         else:
             fus.update(); t_u = fus.timings()["update_ms"]
             fus.extract_raw(); t_e = fus.timings()
@@ -407,11 +407,11 @@ def run_b200(args):
             nb = min(BATCH, N_FRAMES - b)
             fus.push_frames_device(dev_frames[b], nb, npf, 4, poses[b:b + nb], first + b)
 
-    peer = sh.PeerExchange(fus) if world > 1 else None    # receive buffers mapped into every peer (CUDA IPC): the exchange kernel stores over NVLink
+    peer = sh.DeviceExchange(fus) if world > 1 else None  # receive buffers mapped into every peer (CUDA IPC): the exchange kernel stores over NVLink
 
     def process_and_clear(keep=None):
         if world > 1:     # process() across ranks: slab-routed records written straight into the peers' buffers, then slab work
-            n_local, _, tm = sh.merge_and_extract_v2(fus, peer=peer, gather_to=None)     # every rank keeps its own x-slab
+            n_local, _, tm = sh.merge_and_extract_v3(fus, peer=peer, gather_to=None)     # every rank keeps its own x-slab
             fus.clear()
             if keep is not None:
                 nv = torch.tensor([n_local], dtype=torch.int64, device=f"cuda:{local}")
@@ -547,7 +547,7 @@ def run_b200(args):
 
     c3 = None
     if not args.no_c3:
-        c3 = c3_strong(pcf, sh, local, rank, world, lambda f: sh.PeerExchange(f))
+        c3 = c3_strong(pcf, sh, local, rank, world, lambda f: sh.DeviceExchange(f))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -73,8 +73,10 @@ struct pcf_ctx {
     int64_t last_frame_idx = -1;
     int32_t slab_lo = 0, slab_hi = -1;               // x-range owned by this context; hi < 0 = whole grid
     DevBuf dense_log;
-    // frame-sharded exchange
-    ExchangePlan plan{};
+    // frame-sharded exchange: the routing plan, the plane histogram and the row of totals live in device memory
+    DevBuf ex_hist, ex_plan, ex_row;
+    uint32_t ex_ranks = 0;
+    int32_t ex_self = -1;                 // this context's rank in the exchange (-1: unknown, host-driven API)
     bool plan_valid = false;
     void* recv_buf = nullptr;             // receive buffer of the exchange (plain cudaMalloc so that it can be IPC-exported)
     size_t recv_cap = 0;
@@ -618,7 +620,7 @@ void destroy_impl(pcf_ctx* c) {
     DevBuf* bufs[] = {&c->n_cell, &c->n_nrm, &c->n_mark, &c->scan1, &c->scan2, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->hist, &c->sort_tab,
                       &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->sorted, &c->uv_cell, &c->uv_off, &c->nidx, &c->sc_a, &c->sc_b,
                       &c->sc_c, &c->flags, &c->slots, &c->cand, &c->res_dev, &c->total_dev, &c->dense_log, &c->sc_keys, &c->sc_ids,
-                      &c->sc_order, &c->sc_okeys, &c->sc_tab};
+                      &c->sc_order, &c->sc_okeys, &c->sc_tab, &c->ex_hist, &c->ex_plan, &c->ex_row};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     void* raw[] = {c->first_frame, c->holder, c->nrm_bits, c->occ_bits, c->occ_rank, c->vp_table, c->log, c->chunk_count, c->chunk_frame, c->recv_buf};
     for (void* p : raw) if (p) cudaFree(p);
@@ -703,7 +705,7 @@ void pcf_default_config(pcf_config* cfg) {
     cfg->max_frames = 1u << 16;
     cfg->log_capacity_hint = 0;
     cfg->stage_threads = 0;                                   // auto
-    cfg->stage_raw_lanes = 0;                                 // default (2)
+    cfg->stage_raw_lanes = 0;                                 // off
 }
 
 int pcf_create(const pcf_config* cfg, pcf_ctx** out) {
@@ -900,7 +902,9 @@ static int ensure_stager(pcf_ctx* c) {
     if (c->stager) return PCF_OK;
     int threads = c->cfg.stage_threads;
     if (const char* e = getenv("PCF_STAGE_THREADS")) if (atoi(e) > 0) threads = atoi(e);
-    if (threads <= 0) threads = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+    // packing is bound by memory bandwidth, not by cores: 3/4 of the hardware threads saturate it, and a full house makes the
+    // in-order hand-over wait for descheduled stragglers (measured on a 16-vCPU host: 12 threads 6.7 G points/s, 16 threads 5.4 G)
+    if (threads <= 0) threads = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency() * 3u / 4u));
     Stager::Hooks h;
     const int dev = c->device;
     h.alloc_pinned = [](size_t bytes) { return pcf_host_alloc(bytes); };
@@ -910,7 +914,7 @@ static int ensure_stager(pcf_ctx* c) {
     h.push = [c](int s, const float* xyz, uint32_t n_staged, uint32_t n_offered, const double* pose, uint32_t frame_idx) {
         return push_host_cloud_impl(c, xyz, (size_t)n_staged * 12, 0, n_staged, 3, nullptr, pose, nullptr, frame_idx, n_offered, c->slot_ev[s]);
     };
-    int raw_lanes = c->cfg.stage_raw_lanes == 0 ? 2 : std::max(c->cfg.stage_raw_lanes, 0);
+    int raw_lanes = std::max(c->cfg.stage_raw_lanes, 0);
     if (const char* e = getenv("PCF_RAW_LANES")) raw_lanes = std::max(atoi(e), 0);
     h.raw_ok = [](const StageJob& j) {
         if (j.x_offset != 0 || (j.point_step != 16 && j.point_step != 12) || ((uintptr_t)j.data & 15u)) return false;
@@ -1317,24 +1321,88 @@ int pcf_plane_counts(pcf_ctx* c, uint32_t* counts_host) {
 }
 
 // ---- exchange v2: slab-routed records, compaction fused with the (peer) write ---------------------------------
+// Two ways to drive it.  Device-resident (one process per GPU, sharded.py::merge_and_extract_v3): pcf_exchange_hist ->
+// [all-reduce of the histogram in place] -> pcf_exchange_plan -> [all-gather of the row] -> pcf_exchange_scatter_async ->
+// [stream-ordered barrier] -> pcf_install_records; nothing in it waits for the host except the one read-back of the
+// gathered rows that sizes the receive buffers.  Host-driven (several contexts in one process: the C++ replay driver,
+// the emulated-rank tests): pcf_plane_point_counts -> pcf_exchange_counts(bounds) -> pcf_exchange_scatter -> pcf_install_records.
+static int launch_plane_hist(pcf_ctx* c) {
+    const uint32_t np = c->g.n1[0];
+    if ((size_t)np * 4 > 200 * 1024) return fail(c, PCF_ERR_INVALID, "plane histogram: %u x-planes exceed the shared-memory histogram (51200)", np);
+    if ((size_t)np * 4 > 48 * 1024) CU(cudaFuncSetAttribute(k_plane_point_counts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)np * 4));
+    int rc = reserve(c, c->ex_hist, (size_t)np * 8);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(c->ex_hist.p, 0, (size_t)np * 8, c->stream));
+    if (c->n_chunks) {
+        uint32_t grid = std::min<uint32_t>(div_up(c->n_chunks, kWarps), (uint32_t)c->sm_count * 4);
+        k_plane_point_counts<<<grid, kBlock, (size_t)np * 4, c->stream>>>(c->log, c->chunk_count, c->n_chunks, c->g.plane_cells, np,
+                                                                           (unsigned long long*)c->ex_hist.p);
+        c->stats.kernel_launches++;
+        CU(cudaGetLastError());
+    }
+    return PCF_OK;
+}
+
 int pcf_plane_point_counts(pcf_ctx* c, uint32_t* counts_host) {
     if (!c || !counts_host) return PCF_ERR_INVALID;
     ENTER(c);
     CU(cudaStreamSynchronize(c->copy_stream));
-    uint32_t np = c->g.n1[0];
-    if ((size_t)np * 4 > 200 * 1024) return fail(c, PCF_ERR_INVALID, "pcf_plane_point_counts: %u x-planes exceed the shared-memory histogram (51200)", np);
-    if ((size_t)np * 4 > 48 * 1024) CU(cudaFuncSetAttribute(k_plane_point_counts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)np * 4));
-    int rc = reserve(c, c->tmpA, (size_t)np * 4);
+    int rc = launch_plane_hist(c);
     if (rc) return rc;
-    CU(cudaMemsetAsync(c->tmpA.p, 0, (size_t)np * 4, c->stream));
-    if (c->n_chunks) {
-        uint32_t grid = std::min<uint32_t>(div_up(c->n_chunks, kWarps), (uint32_t)c->sm_count * 4);
-        k_plane_point_counts<<<grid, kBlock, (size_t)np * 4, c->stream>>>(c->log, c->chunk_count, c->n_chunks, c->g.plane_cells, np, (uint32_t*)c->tmpA.p);
-        c->stats.kernel_launches++;
-        CU(cudaGetLastError());
-    }
-    CU(cudaMemcpyAsync(counts_host, c->tmpA.p, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream));
+    const uint32_t np = c->g.n1[0];
+    std::vector<unsigned long long> h(np);
+    CU(cudaMemcpyAsync(h.data(), c->ex_hist.p, (size_t)np * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    for (uint32_t i = 0; i < np; i++) counts_host[i] = (uint32_t)h[i];
+    return PCF_OK;
+}
+
+int pcf_exchange_hist(pcf_ctx* c, void** hist_dev, uint32_t* n_planes) {
+    if (!c || !hist_dev || !n_planes) return PCF_ERR_INVALID;
+    ENTER(c);
+    if (c->n_normals) return fail(c, PCF_ERR_INVALID, "exchange after pcf_update: sharded merge of interleaved schedules is not supported");
+    if (c->log_installed) return fail(c, PCF_ERR_INVALID, "exchange after pcf_install_records / pcf_log_replace: the installed log has lost its per-chunk frame indices; pcf_clear first");
+    int rc = launch_plane_hist(c);
+    if (rc) return rc;
+    *hist_dev = c->ex_hist.p;
+    *n_planes = c->g.n1[0];
+    return PCF_OK;
+}
+
+// counts of this rank's records per destination, from the plan in c->ex_plan -> c->ex_row (device): [R totals | R + 1 bounds]
+static int exchange_count_row(pcf_ctx* c, int32_t n_ranks) {
+    int rc;
+    if ((rc = reserve(c, c->ex_row, (size_t)(2 * kMaxRanks + 1) * 8))) return rc;
+    const size_t n = (size_t)n_ranks * c->n_chunks;
+    if ((rc = reserve(c, c->tmpC, (n + 1) * 4))) return rc;
+    if ((rc = reserve(c, c->tmpD, (n + 1) * 4))) return rc;
+    uint32_t* cnt = (uint32_t*)c->tmpC.p;
+    uint32_t* off = (uint32_t*)c->tmpD.p;
+    if (c->n_chunks) {
+        LAUNCH(c, k_exchange_count, div_up(c->n_chunks, kWarps), kBlock, c->log, c->chunk_count, c->n_chunks, (const ExchangePlan*)c->ex_plan.p, cnt);
+        CU(cudaMemsetAsync(cnt + n, 0, 4, c->stream));
+        if ((rc = scan_u32(c, cnt, off, n + 1, nullptr))) return rc;       // off[n] = grand total
+    }
+    LAUNCH(c, k_exchange_row, 1, 32, (const uint32_t*)off, c->n_chunks, (const ExchangePlan*)c->ex_plan.p, (long long*)c->ex_row.p);
+    CU(cudaGetLastError());
+    c->ex_ranks = (uint32_t)n_ranks;
+    c->plan_valid = true;
+    return PCF_OK;
+}
+
+int pcf_exchange_plan(pcf_ctx* c, int32_t n_ranks, int32_t self, void** row_dev) {
+    if (!c || !row_dev || n_ranks < 1 || n_ranks > kMaxRanks || self < 0 || self >= n_ranks)
+        return c ? fail(c, PCF_ERR_INVALID, "bad exchange arguments (1..%d ranks)", kMaxRanks) : PCF_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    if (!c->ex_hist.p) return fail(c, PCF_ERR_INVALID, "pcf_exchange_plan without pcf_exchange_hist");
+    int rc = reserve(c, c->ex_plan, sizeof(ExchangePlan));
+    if (rc) return rc;
+    const int32_t halo = std::max(c->g.walk_k, 2);      // +-K walk (OG.hpp:403-405) and the 5x5x5 scan (OG.hpp:334)
+    LAUNCH(c, k_slab_bounds, 1, 1024, (const unsigned long long*)c->ex_hist.p, c->g.n1[0], (uint32_t)n_ranks, (uint32_t)halo, c->g.plane_cells,
+           (ExchangePlan*)c->ex_plan.p);
+    if ((rc = exchange_count_row(c, n_ranks))) return rc;
+    c->ex_self = self;
+    *row_dev = c->ex_row.p;
     return PCF_OK;
 }
 
@@ -1345,7 +1413,7 @@ int pcf_exchange_counts(pcf_ctx* c, const int32_t* bounds, int32_t n_ranks, uint
     if (c->n_normals) return fail(c, PCF_ERR_INVALID, "exchange after pcf_update: sharded merge of interleaved schedules is not supported");
     if (c->log_installed) return fail(c, PCF_ERR_INVALID, "exchange after pcf_install_records / pcf_log_replace: the installed log has lost its per-chunk frame indices; pcf_clear first");
     const int32_t halo = std::max(c->g.walk_k, 2);      // +-K walk (OG.hpp:403-405) and the 5x5x5 scan (OG.hpp:334)
-    ExchangePlan& p = c->plan;
+    ExchangePlan p{};
     p.n_ranks = (uint32_t)n_ranks;
     p.plane_cells = c->g.plane_cells;
     for (int d = 0; d < n_ranks; d++) {
@@ -1353,44 +1421,40 @@ int pcf_exchange_counts(pcf_ctx* c, const int32_t* bounds, int32_t n_ranks, uint
         bool empty = bounds[d] == bounds[d + 1];
         p.lo[d] = empty ? 0u : (uint32_t)std::max<int32_t>(bounds[d] - halo, 0);
         p.hi[d] = empty ? 0u : (uint32_t)std::min<int64_t>((int64_t)bounds[d + 1] + halo, c->g.n1[0]);
-        p.dst[d] = nullptr;
+        p.bounds[d] = bounds[d];
     }
-    for (int d = 0; d < n_ranks; d++) counts_host[d] = 0;
-    c->plan_valid = true;
-    if (!c->n_chunks) return PCF_OK;
-    size_t n = (size_t)n_ranks * c->n_chunks;
-    int rc;
-    if ((rc = reserve(c, c->tmpC, (n + 1) * 4))) return rc;
-    if ((rc = reserve(c, c->tmpD, (n + 1) * 4))) return rc;
-    uint32_t* cnt = (uint32_t*)c->tmpC.p;
-    uint32_t* off = (uint32_t*)c->tmpD.p;
-    LAUNCH(c, k_exchange_count, div_up(c->n_chunks, kWarps), kBlock, c->log, c->chunk_count, c->n_chunks, p, cnt);
-    CU(cudaMemsetAsync(cnt + n, 0, 4, c->stream));
-    if ((rc = scan_u32(c, cnt, off, n + 1, nullptr))) return rc;       // off[n] = grand total
-    // per-destination totals = off[(d+1) * n_chunks] - off[d * n_chunks]
-    std::vector<uint32_t> edge((size_t)n_ranks + 1);
-    for (int d = 0; d <= n_ranks; d++)
-        CU(cudaMemcpyAsync(&edge[d], off + (size_t)d * c->n_chunks, 4, cudaMemcpyDeviceToHost, c->stream));
+    p.bounds[n_ranks] = bounds[n_ranks];
+    int rc = reserve(c, c->ex_plan, sizeof(ExchangePlan));
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->ex_plan.p, &p, sizeof p, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));               // `p` is a stack object
+    if ((rc = exchange_count_row(c, n_ranks))) return rc;
+    c->ex_self = -1;
+    long long row[2 * kMaxRanks + 1];
+    CU(cudaMemcpyAsync(row, c->ex_row.p, (size_t)(2 * n_ranks + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    for (int d = 0; d < n_ranks; d++) counts_host[d] = edge[d + 1] - edge[d];
-    c->stats.d2h_bytes += 4 * (n_ranks + 1);
+    for (int d = 0; d < n_ranks; d++) counts_host[d] = (uint64_t)row[d];
+    c->stats.d2h_bytes += 8 * (2 * n_ranks + 1);
     return PCF_OK;
 }
 
-int pcf_exchange_scatter(pcf_ctx* c, void* const* dst_bufs, const uint64_t* dst_offsets) {
+static int exchange_scatter_impl(pcf_ctx* c, void* const* dst_bufs, const uint64_t* dst_offsets, bool sync) {
     if (!c || !dst_bufs || !dst_offsets) return PCF_ERR_INVALID;
-    if (!c->plan_valid) return fail(c, PCF_ERR_INVALID, "pcf_exchange_scatter without pcf_exchange_counts");
+    if (!c->plan_valid) return fail(c, PCF_ERR_INVALID, "pcf_exchange_scatter without pcf_exchange_counts / pcf_exchange_plan");
     CU(cudaSetDevice(c->device));
-    for (uint32_t d = 0; d < c->plan.n_ranks; d++) c->plan.dst[d] = (float4*)dst_bufs[d] + dst_offsets[d];
+    ExchangeDst to{};
+    for (uint32_t d = 0; d < c->ex_ranks; d++) to.dst[d] = (float4*)dst_bufs[d] + dst_offsets[d];
     if (c->n_chunks) {
-        LAUNCH(c, k_exchange_scatter, div_up(c->n_chunks, kWarps), kBlock, c->log, c->chunk_count, c->chunk_frame, c->n_chunks, c->plan,
-               (const uint32_t*)c->tmpD.p);
+        LAUNCH(c, k_exchange_scatter, div_up(c->n_chunks, kWarps), kBlock, c->log, c->chunk_count, c->chunk_frame, c->n_chunks,
+               (const ExchangePlan*)c->ex_plan.p, to, (const uint32_t*)c->tmpD.p);
         CU(cudaGetLastError());
     }
-    CU(cudaStreamSynchronize(c->stream));      // the caller's barrier across ranks comes next
+    if (sync) CU(cudaStreamSynchronize(c->stream));     // host-driven callers: the barrier across ranks comes next
     c->plan_valid = false;
     return PCF_OK;
 }
+int pcf_exchange_scatter(pcf_ctx* c, void* const* dst_bufs, const uint64_t* dst_offsets) { return exchange_scatter_impl(c, dst_bufs, dst_offsets, true); }
+int pcf_exchange_scatter_async(pcf_ctx* c, void* const* dst_bufs, const uint64_t* dst_offsets) { return exchange_scatter_impl(c, dst_bufs, dst_offsets, false); }
 
 int pcf_recv_buffer(pcf_ctx* c, uint64_t n_records, void** dev_ptr) {
     if (!c || !dev_ptr) return PCF_ERR_INVALID;
@@ -1470,21 +1534,30 @@ int pcf_install_records(pcf_ctx* c, const void* records_dev, uint64_t n) {
     if (c->n_normals) return fail(c, PCF_ERR_INVALID, "pcf_install_records after pcf_update: sharded merge of interleaved schedules is not supported");
     ENTER(c);
     c->log_installed = true;
-    CU(cudaStreamSynchronize(c->copy_stream));
     uint32_t chunks = div_up(n, kWChunk);
     if (chunks > kMaxChunks) return fail(c, PCF_ERR_CAPACITY, "point log limit reached");
+    const bool keep_region = c->ex_self >= 0 && c->ex_plan.p;     // device-resident exchange: this rank's region is known
+    if (keep_region) {
+        // the own cells inside slab + halo stay (the routed records include them), the own cells outside are emptied
+        if (c->n_chunks)
+            LAUNCH(c, k_unmark_outside, div_up(c->n_chunks, kWarps), kBlock, c->log, c->chunk_count, c->n_chunks, c->g, (const ExchangePlan*)c->ex_plan.p,
+                   (uint32_t)c->ex_self, c->first_frame, c->occ_bits);
+    } else {
+        CU(cudaStreamSynchronize(c->copy_stream));
+        LAUNCH(c, k_fill_u32, 148 * 8, 512, c->first_frame, c->g.phys_cells, kEmpty);
+        CU(cudaMemsetAsync(c->occ_bits, 0, (c->n_words + 2) * 4, c->stream));
+    }
     c->n_chunks = 0;                       // the local log is superseded by the routed records (own ones included)
     int rc = ensure_log(c, std::max<uint32_t>(chunks, 1));
     if (rc) return rc;
-    LAUNCH(c, k_fill_u32, 148 * 8, 512, c->first_frame, c->g.phys_cells, kEmpty);
-    CU(cudaMemsetAsync(c->occ_bits, 0, (c->n_words + 2) * 4, c->stream));
     if (n) {
         LAUNCH(c, k_install_records, div_up(n, kBlock), kBlock, (const float4*)records_dev, n, c->g, c->first_frame, c->occ_bits, c->log);
         LAUNCH(c, k_chunk_counts_dense, div_up(chunks, kBlock), kBlock, c->chunk_count, chunks, n);
         CU(cudaGetLastError());
     }
     c->n_chunks = chunks;
-    CU(cudaStreamSynchronize(c->stream));
+    if (!keep_region) CU(cudaStreamSynchronize(c->stream));
+    c->ex_self = -1;
     c->occ_dirty = true;
     c->sorted_valid = false;
     return PCF_OK;

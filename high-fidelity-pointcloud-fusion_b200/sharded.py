@@ -152,6 +152,50 @@ def merge_and_extract_local_v2(ranks):
     return _concat_results(parts)
 
 
+def merge_and_extract_local_v3(ranks):
+    """In-process emulation of the device-resident exchange (merge_and_extract_v3): the same library calls -- histogram,
+    device-side slab bounds + routing counts, asynchronous scatter, region-keeping install -- with the collectives replaced
+    by plain tensor sums / copies between the contexts of this process.  Also returns the bounds the device chose."""
+    world = len(ranks)
+    devs = [torch.device("cuda", f.device_index) for f in ranks]
+    hists = []
+    for f, d in zip(ranks, devs):
+        hp, n_planes = f.exchange_hist()
+        f.sync()
+        hists.append(_as_tensor(hp, (n_planes,), "<i8", d))
+    total_hist = sum(h.to(devs[0]) for h in hists)                   # the all-reduce
+    vps = None
+    for f, d in zip(ranks, devs):
+        vp, nf = f.viewpoint_table()
+        v = _as_tensor(vp, (nf, 4), "<f4", d).to(devs[0])
+        vps = v.clone() if vps is None else vps + v
+    rows = []
+    for r, (f, d, h) in enumerate(zip(ranks, devs, hists)):
+        h.copy_(total_hist.to(d))
+        vp, nf = f.viewpoint_table()
+        _as_tensor(vp, (nf, 4), "<f4", d).copy_(vps.to(d))
+        torch.cuda.synchronize(d)
+        row = _as_tensor(f.exchange_plan(world, r), (2 * world + 1,), "<i8", d)
+        f.sync()
+        rows.append(row.cpu().numpy().copy())                         # the all-gather
+    rows = np.stack(rows)
+    off, total = route_offsets(rows[:, :world])
+    bounds = [int(b) for b in rows[0, world:]]
+    assert all([int(b) for b in rr[world:]] == bounds for rr in rows)
+    bufs = [f.recv_buffer(int(total[r])) for r, f in enumerate(ranks)]
+    for s, f in enumerate(ranks):
+        f.exchange_scatter_async(bufs, off[s])
+    for f in ranks:
+        f.sync()                                                      # the barrier
+    parts = []
+    for r, f in enumerate(ranks):
+        f.install_records(bufs[r], int(total[r]))
+        f.set_slab(bounds[r], bounds[r + 1])
+        f.update()
+        parts.append(f.extract())
+    return _concat_results(parts), bounds
+
+
 class PeerExchange:
     """One process per GPU: receive buffers mapped into every peer with CUDA IPC, so that pcf_exchange_scatter's stores
     travel over NVLink.  Handles are re-exchanged only when a receive buffer had to grow."""
@@ -175,6 +219,82 @@ class PeerExchange:
             dist.all_gather_object(handles, self.fus.ipc_export(), group=self.group)
             self.ptrs = [mine if r == self.rank else self.fus.ipc_open(handles[r]) for r in range(self.world)]
         return self.ptrs
+
+
+class DeviceExchange(PeerExchange):
+    """State of the device-resident exchange (merge_and_extract_v3): the IPC-mapped receive buffers, a pinned landing zone
+    for the gathered rows, and the token of the stream-ordered barrier.  Receive-buffer capacities are tracked for EVERY
+    rank with the same rule on every rank, so that all ranks agree on when to re-map without talking to each other."""
+
+    def __init__(self, fus, group=None):
+        super().__init__(fus, group)
+        dev = torch.device("cuda", fus.device_index)
+        self.rows_host = torch.empty((self.world, 2 * self.world + 1), dtype=torch.int64).pin_memory()
+        self.rows_dev = torch.empty((self.world, 2 * self.world + 1), dtype=torch.int64, device=dev)
+        self.token = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.caps = [-1] * self.world
+        self.ev = torch.cuda.Event()
+
+    def buffers_for(self, totals):
+        import torch.distributed as dist
+        if self.ptrs is None or any(int(t) > c for t, c in zip(totals, self.caps)):
+            self.caps = [max(int(t) + int(t) // 4, 1 << 16, c) for t, c in zip(totals, self.caps)]
+            self.fus.sync()
+            self.fus.ipc_close_all()
+            dist.barrier(group=self.group)     # no rank may free its exported buffer while a peer still has it mapped
+            mine = self.fus.recv_buffer(self.caps[self.rank])
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self.fus.ipc_export(), group=self.group)
+            self.ptrs = [mine if r == self.rank else self.fus.ipc_open(handles[r]) for r in range(self.world)]
+        return self.ptrs
+
+
+def merge_and_extract_v3(fus, group=None, gather_to=None, peer=None):
+    """One process per GPU, device-resident exchange.  Every step is enqueued on the context's stream -- the plane histogram,
+    its all-reduce, the slab bounds + routing counts (computed on the device), the all-gather of the rows, the ONE compaction
+    kernel that stores into the peers' buffers over NVLink, a one-word all-reduce as the stream-ordered barrier, the install
+    -- and the host waits exactly once, for the gathered R x (2R+1) rows that size the receive buffers.
+    Returns (local slab result or voxel count, merged result on rank `gather_to` else None, timings dict in ms)."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device("cuda", fus.device_index)
+    peer = peer or DeviceExchange(fus, group)
+    stream = torch.cuda.ExternalStream(fus.stream, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    with torch.cuda.stream(stream):          # torch's collectives order themselves against the CURRENT stream = the library's
+        ev[0].record()
+        hp, n_planes = fus.exchange_hist()
+        dist.all_reduce(_as_tensor(hp, (n_planes,), "<i8", dev), group=group)
+        vp, nf = fus.viewpoint_table()
+        dist.all_reduce(_as_tensor(vp, (nf, 4), "<f4", dev), group=group)      # disjoint per-frame rows: the sum is exact
+        row = _as_tensor(fus.exchange_plan(world, rank), (2 * world + 1,), "<i8", dev)
+        dist.all_gather_into_tensor(peer.rows_dev, row, group=group)
+        peer.rows_host.copy_(peer.rows_dev, non_blocking=True)
+        peer.ev.record()
+    peer.ev.synchronize()                    # the one host wait of the exchange
+    rows = peer.rows_host.numpy()
+    off, total = route_offsets(rows[:, :world])
+    bounds = [int(b) for b in rows[rank, world:]]
+    ptrs = peer.buffers_for(total)
+    with torch.cuda.stream(stream):
+        fus.exchange_scatter_async(ptrs, off[rank])
+        dist.all_reduce(peer.token, group=group)          # stream-ordered barrier: every rank's peer stores have landed
+        ev[1].record()
+    fus.install_records(ptrs[rank], int(total[rank]))
+    fus.set_slab(bounds[rank], bounds[rank + 1])
+    fus.update()
+    local = fus.extract() if gather_to is not None else fus.extract_raw()
+    with torch.cuda.stream(stream):
+        ev[2].record()
+    torch.cuda.synchronize(dev)
+    timings = {"exchange_ms": ev[0].elapsed_time(ev[1]), "slab_process_ms": ev[1].elapsed_time(ev[2]),
+               "records_in": int(total[rank]), "records_out": int(rows[rank, :world].sum())}
+    if gather_to is None:                      # every rank keeps (or writes) its own slab: no result traffic at all
+        return local, None, timings
+    parts = [None] * world if rank == gather_to else None
+    dist.gather_object(local, parts, dst=gather_to, group=group)
+    full = _concat_results(parts) if rank == gather_to else None
+    return local, full, timings
 
 
 def merge_and_extract_v2(fus, group=None, gather_to=0, peer=None):

@@ -56,10 +56,11 @@ typedef struct {
     uint32_t max_frames;         /* size of the frame/viewpoint table (frame_idx < max_frames) */
     uint64_t log_capacity_hint;  /* initial point-log capacity in INPUT points; grows on demand */
     int32_t stage_threads;       /* host staging threads of pcf_submit_* (the reference has ONE addPoints thread,
-                                    node.cpp:166,218); 0 = min(16, hardware threads); env PCF_STAGE_THREADS overrides */
+                                    node.cpp:166,218); 0 = min(16, 3/4 of the hardware threads); env PCF_STAGE_THREADS overrides */
     int32_t stage_raw_lanes;     /* extra threads that upload pinned float4 / xyz clouds UNSTAGED while clouds pile up behind the
-                                    packers, using the PCIe time the staged copies leave free; 0 = default (2), < 0 = none;
-                                    env PCF_RAW_LANES overrides */
+                                    packers, using the PCIe time the staged copies leave free; 0 = none (default: on hosts whose
+                                    memory bandwidth bounds the packers the extra DMA traffic costs more than it brings, see
+                                    DESIGN.md); env PCF_RAW_LANES overrides */
 } pcf_config;
 
 /* Extraction output, structure of arrays, x-major voxel order = the reference's scan order
@@ -229,6 +230,19 @@ int pcf_plane_counts(pcf_ctx* ctx, uint32_t* counts_host);
 int pcf_plane_point_counts(pcf_ctx* ctx, uint32_t* counts_host /* xdim+1 entries */);
 int pcf_exchange_counts(pcf_ctx* ctx, const int32_t* bounds /* n_ranks+1 */, int32_t n_ranks, uint64_t* counts_host /* n_ranks */);
 int pcf_exchange_scatter(pcf_ctx* ctx, void* const* dst_bufs /* n_ranks device pointers */, const uint64_t* dst_offsets /* records */);
+/* Device-resident variant (one process per GPU): nothing below waits for the host.
+ *   pcf_exchange_hist   per-plane record histogram of this rank, uint64[n_planes] in device memory, computed on pcf_stream;
+ *                       the caller all-reduces (SUM) it IN PLACE across ranks, stream-ordered after pcf_stream.
+ *   pcf_exchange_plan   slab bounds from the reduced histogram (k_slab_bounds), routing counts, and the row this rank
+ *                       contributes to the all-gather: int64[2 * n_ranks + 1] = [records to every destination | bounds]
+ *                       in device memory.  The gathered n_ranks x n_ranks totals give every (source, destination) offset.
+ *   pcf_exchange_scatter_async   as pcf_exchange_scatter without the trailing stream synchronisation; the caller orders the
+ *                       peers' install after it with a stream-ordered collective.
+ *   pcf_install_records after pcf_exchange_plan keeps the own cells inside slab + halo and empties the own cells outside
+ *                       (one pass over the own log) instead of refilling the dense grid, and does not synchronise. */
+int pcf_exchange_hist(pcf_ctx* ctx, void** hist_dev, uint32_t* n_planes);
+int pcf_exchange_plan(pcf_ctx* ctx, int32_t n_ranks, int32_t self, void** row_dev);
+int pcf_exchange_scatter_async(pcf_ctx* ctx, void* const* dst_bufs, const uint64_t* dst_offsets);
 int pcf_recv_buffer(pcf_ctx* ctx, uint64_t n_records, void** dev_ptr);
 int pcf_ipc_export(pcf_ctx* ctx, void* handle64);                          /* cudaIpcMemHandle_t of the receive buffer */
 int pcf_ipc_open(pcf_ctx* ctx, const void* handle64, void** peer_ptr);

@@ -201,6 +201,36 @@ def test_exchange_v2_slab_routed_records_byte_identical(pcf, small, world):
         f.close()
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_device_resident_exchange_byte_identical_and_same_bounds_as_host_rule(pcf, small, world):
+    """The device-resident exchange (pcf_exchange_hist / _plan / _scatter_async + region-keeping install): slab bounds computed
+    by k_slab_bounds equal the host rule (sharded.choose_slabs on the summed histogram), a second round after clear() reuses
+    every buffer, and the merged extraction is byte-identical to one context fed every frame."""
+    import importlib
+    sh = importlib.import_module(pcf.__name__ + ".sharded")
+    g = small.grid
+    frames = [small.frame(i) for i in range(small.n_frames)]
+    one = pcf.Fusion(g.box, g.res)
+    for i, (pts, T) in enumerate(frames):
+        one.push_frame(pts, T, i)
+    one.update()
+    want = one.extract()
+    ranks = [pcf.Fusion(g.box, g.res) for _ in range(world)]
+    for rnd in range(2):
+        for r, f in enumerate(ranks):
+            lo, hi = sh.frame_block(len(frames), r, world)
+            for i in range(lo, hi):
+                f.push_frame(frames[i][0], frames[i][1], i)
+        plane = sum(f.plane_point_counts().astype(np.int64) for f in ranks)
+        got, bounds = sh.merge_and_extract_local_v3(ranks)
+        assert bounds == sh.slab_bounds_from_points(plane, world)
+        assert_same(got, want, RESULT_FIELDS, f"device-resident exchange x{world} round {rnd}: ")
+        for f in ranks:
+            f.clear()
+    for f in ranks + [one]:
+        f.close()
+
+
 def test_pointcloud2_front_end_and_add_points(pcf, oracle, small):
     """a1 (node.cpp:182-216): a RealSense-style PointCloud2 (x y z at bytes 0/4/8, rgb at 16, point_step 20, padded
     rows) gives the same grid as the float4 path; pcf_add_points (OG.hpp:185 verbatim) equals the oracle's world-frame

@@ -22,7 +22,7 @@ def small(pcf):
 @pytest.mark.parametrize("threads,raw_lanes,pinned", [(1, -1, False), (5, -1, False), (1, 2, True), (3, 1, True), (2, 0, False)])
 @pytest.mark.parametrize("update_every", [None, 2])
 def test_submit_frame_bit_identical_to_push_frame_and_oracle(pcf, oracle, small, threads, raw_lanes, pinned, update_every):
-    """raw_lanes: -1 none; 2 / 1 with pinned clouds: some clouds are uploaded unstaged by the raw lanes while the packers are
+    """raw_lanes: -1 / 0 none; 2 / 1 with pinned clouds: some clouds are uploaded unstaged by the raw lanes while the packers are
     busy (which ones depends on timing -- the grid must not); pageable clouds are always packed."""
     import torch
     g = small.grid

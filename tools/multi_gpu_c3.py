@@ -49,13 +49,13 @@ def ingest(fus, lo, hi, batch=125):
 
 lo, hi = sh.frame_block(n_frames, rank, world)
 fus = pcf.Fusion(g.box, g.res, device=local, max_frames=max(1 << 16, n_frames + 1), log_capacity_hint=(hi - lo) * npf)
-peer = sh.PeerExchange(fus)
+peer = sh.DeviceExchange(fus)
 line = {}
 for rep in range(2):                       # second repetition = warm buffers
     ms = ingest(fus, lo, hi)
     dist.barrier()
     t0 = time.perf_counter()
-    _, _, tm = sh.merge_and_extract_v2(fus, peer=peer, gather_to=None)     # every rank keeps its own x-slab
+    _, _, tm = sh.merge_and_extract_v3(fus, peer=peer, gather_to=None)     # every rank keeps its own x-slab
     dist.barrier()
     wall = (time.perf_counter() - t0) * 1e3
     if rep == 1:

@@ -15,12 +15,12 @@ ok = True
 for name, scene in [("small_sphere", synth.small_sphere(12)), ("sphere 640x480 1 mm", synth.sphere_turntable(16))]:
     g = scene.grid
     fus = pcf.Fusion(g.box, g.res, device=local)
-    peer = sh.PeerExchange(fus)
+    peer = sh.DeviceExchange(fus)
     lo, hi = sh.frame_block(scene.n_frames, rank, world)
     for i in range(lo, hi):
         fus.push_frame(*scene.frame(i), i)
     for rep in range(2):                     # twice: the second round reuses the mapped buffers
-        _, full, tm = sh.merge_and_extract_v2(fus, peer=peer)
+        _, full, tm = sh.merge_and_extract_v3(fus, peer=peer, gather_to=0)
         if rank == 0:
             one = pcf.Fusion(g.box, g.res, device=local)
             for i in range(scene.n_frames):
