@@ -269,6 +269,15 @@ class Fusion:
     def drain(self):
         self._ck(self.lib.pcf_drain(self.h))
 
+    def wait_staged(self, n):
+        """Block until `n` submitted clouds have been handed to the GPU (or nothing is pending)."""
+        self._ck(self.lib.pcf_wait_staged(self.h, int(n)))
+
+    def staged_count(self) -> int:
+        n = C.c_uint64()
+        self._ck(self.lib.pcf_staged_count(self.h, C.byref(n)))
+        return int(n.value)
+
     def stage_frame(self, pts, out=None):
         """pcf_stage_frame: clip-and-pack on the calling thread.  Returns (staged float32 [m, 3], m)."""
         n, stride = pts.shape

@@ -115,6 +115,8 @@ def test_reset_closes_the_gate_and_drops_only_untaken_clouds(pcf, small):
     poses = [np.ascontiguousarray(T, np.float64).reshape(16) for _, T in clouds]
     for i in range(4):
         assert f.submit_frame(clouds[i][0], poses[i], i) == 0
+    f.wait_staged(1)                                                 # the staging thread has taken (and handed over) the first cloud
+    assert f.staged_count() >= 1
     f.reset()
     assert f.submit_frame(clouds[4][0], poses[4], 4) == 1            # PCF_DROPPED: the gate is closed
     assert f.push_frame(clouds[4][0], clouds[4][1], 4) == 1
