@@ -250,6 +250,8 @@ def multi_gpu_parity(pcf, sh, local, rank, world):
             ok &= same
             detail.append({"update_every": update_every, "voxels": len(want), "byte_identical": bool(same)})
             one.close()
+        torch.cuda.synchronize()
+        del peer
         fus.close()
     flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=f"cuda:{local}")
     dist.broadcast(flag, 0)
@@ -320,6 +322,8 @@ def c3_strong(pcf, sh, local, rank, world, peer_factory):
                    "frames": C3_FRAMES, "ingest_ms_max_rank": float(t[0]), "ingest_pts_s": C3_FRAMES * npf / (float(t[0]) * 1e-3),
                    "process_ms": wall, "exchange_ms": float(t[1]), "slab_ms": float(t[2]), "voxels": got[0], "checksums": got}
         fus.clear()
+    torch.cuda.synchronize()
+    del peer
     fus.close()
     if world > 1:
         # rank 0 integrates ALL frames alone: the sharded extraction must have the same count and checksums
@@ -541,6 +545,8 @@ def run_b200(args):
                 "algorithmic_bytes_per_launch": alg_bytes_step / launches_per_step, "launch_ms": per_launch_ms,
                 "kept_fraction": kept / points_per_step}
 
+    torch.cuda.synchronize()
+    del peer
     fus.close()
     del dev_frames, host_frames, host_list
     torch.cuda.empty_cache()

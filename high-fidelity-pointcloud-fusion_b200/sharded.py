@@ -229,11 +229,9 @@ class DeviceExchange(PeerExchange):
     def __init__(self, fus, group=None):
         super().__init__(fus, group)
         dev = torch.device("cuda", fus.device_index)
-        self.rows_host = torch.empty((self.world, 2 * self.world + 1), dtype=torch.int64).pin_memory()
         self.rows_dev = torch.empty((self.world, 2 * self.world + 1), dtype=torch.int64, device=dev)
         self.token = torch.zeros(1, dtype=torch.int32, device=dev)
         self.caps = [-1] * self.world
-        self.ev = torch.cuda.Event()
 
     def buffers_for(self, totals):
         import torch.distributed as dist
@@ -269,10 +267,10 @@ def merge_and_extract_v3(fus, group=None, gather_to=None, peer=None):
         dist.all_reduce(_as_tensor(vp, (nf, 4), "<f4", dev), group=group)      # disjoint per-frame rows: the sum is exact
         row = _as_tensor(fus.exchange_plan(world, rank), (2 * world + 1,), "<i8", dev)
         dist.all_gather_into_tensor(peer.rows_dev, row, group=group)
-        peer.rows_host.copy_(peer.rows_dev, non_blocking=True)
-        peer.ev.record()
-    peer.ev.synchronize()                    # the one host wait of the exchange
-    rows = peer.rows_host.numpy()
+        # the one host wait of the exchange.  (A plain synchronous copy on purpose: a non_blocking copy into a pinned tensor
+        # makes torch's host allocator remember this -- externally owned -- stream and record an event on it when the tensor
+        # is freed, which may be after the context was destroyed.)
+        rows = peer.rows_dev.cpu().numpy()
     off, total = route_offsets(rows[:, :world])
     bounds = [int(b) for b in rows[rank, world:]]
     ptrs = peer.buffers_for(total)
