@@ -20,6 +20,7 @@ _LIBS = {
     "ref": (os.path.join(_HERE, "_ref", "libogref.so"), "ref_"),
     "ref_ordered": (os.path.join(_HERE, "_ref", "libogref_ordered.so"), "ref_"),
     "ref_timing": (os.path.join(_HERE, "_ref", "libogref_timing.so"), "ref_"),
+    "ref_libmtrig": (os.path.join(_HERE, "_ref", "libogref_libmtrig.so"), "ref_"),
 }
 _loaded = {}
 
