@@ -48,7 +48,7 @@ ABI_SYMBOLS = [
     "pcf_default_config", "pcf_create", "pcf_destroy", "pcf_last_error", "pcf_dims", "pcf_start", "pcf_stop", "pcf_reset",
     "pcf_push_frame", "pcf_push_pointcloud2", "pcf_add_points", "pcf_submit_frame", "pcf_submit_pointcloud2", "pcf_drain", "pcf_stage_frame", "pcf_staged_count", "pcf_wait_staged", "pcf_host_alloc", "pcf_host_free", "pcf_upload_ticket", "pcf_wait_upload", "pcf_push_frames_device", "pcf_sync", "pcf_count_kept", "pcf_update", "pcf_extract", "pcf_process", "pcf_write_result",
     "pcf_extract_hq", "pcf_clear", "pcf_dump_state", "pcf_get_stats", "pcf_reset_stats", "pcf_last_timings", "pcf_stream",
-    "pcf_grid_buffer", "pcf_viewpoint_table", "pcf_log_compact", "pcf_log_replace", "pcf_set_slab", "pcf_plane_counts", "pcf_plane_point_counts", "pcf_exchange_counts", "pcf_exchange_scatter", "pcf_exchange_hist", "pcf_exchange_plan", "pcf_exchange_scatter_async", "pcf_recv_buffer", "pcf_ipc_export", "pcf_ipc_open",
+    "pcf_grid_buffer", "pcf_viewpoint_table", "pcf_log_compact", "pcf_log_replace", "pcf_set_slab", "pcf_plane_counts", "pcf_plane_point_counts", "pcf_exchange_counts", "pcf_exchange_scatter", "pcf_exchange_hist", "pcf_exchange_plan", "pcf_exchange_scatter_async", "pcf_round_export", "pcf_round_install", "pcf_update_local", "pcf_update_commit", "pcf_recv_buffer", "pcf_ipc_export", "pcf_ipc_open",
     "pcf_ipc_close_all", "pcf_install_records", "pcf_get_viewpoints", "pcf_set_viewpoints", "pcf_enable_peer_access", "pcf_kat_transform_voxel",
     "pcf_kat_normal", "pcf_kat_score", "pcf_kat_format_float", "pcf_kat_clip_pack", "pcf_kat_div",
 ]
@@ -112,6 +112,10 @@ def load_library():
     lib.pcf_exchange_scatter.argtypes = [vp, vp, vp]
     lib.pcf_exchange_scatter_async.argtypes = [vp, vp, vp]
     lib.pcf_exchange_hist.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint32)]
+    lib.pcf_round_export.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
+    lib.pcf_round_install.argtypes = [vp, vp, C.c_uint64]
+    lib.pcf_update_local.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint32)]
+    lib.pcf_update_commit.argtypes = [vp, vp, vp, C.c_uint32]
     lib.pcf_exchange_plan.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(vp)]
     lib.pcf_recv_buffer.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
     lib.pcf_ipc_export.argtypes = [vp, vp]
@@ -394,6 +398,23 @@ class Fusion:
         p = np.ascontiguousarray(dst_ptrs, np.uint64)
         o = np.ascontiguousarray(dst_offsets, np.uint64)
         self._ck(self.lib.pcf_exchange_scatter(self.h, p.ctypes.data, o.ctypes.data))
+
+    # ---- interleaved schedules across ranks (replicated state) ----
+    def round_export(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(self.lib.pcf_round_export(self.h, C.byref(p), C.byref(n)))
+        return p.value, int(n.value)
+
+    def round_install(self, records_dev, n):
+        self._ck(self.lib.pcf_round_install(self.h, _ptr(records_dev), int(n)))
+
+    def update_local(self):
+        pc, pn, n = C.c_void_p(), C.c_void_p(), C.c_uint32()
+        self._ck(self.lib.pcf_update_local(self.h, C.byref(pc), C.byref(pn), C.byref(n)))
+        return pc.value, pn.value, int(n.value)
+
+    def update_commit(self, cells_dev, normals_dev, n):
+        self._ck(self.lib.pcf_update_commit(self.h, _ptr(cells_dev), _ptr(normals_dev), int(n)))
 
     def exchange_hist(self):
         p, n = C.c_void_p(), C.c_uint32()

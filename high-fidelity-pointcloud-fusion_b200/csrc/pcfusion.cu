@@ -65,8 +65,13 @@ struct pcf_ctx {
     uint32_t* chunk_count = nullptr;
     uint32_t* chunk_frame = nullptr;      // frame_idx of every log chunk (the exchange ships it with the records)
     uint32_t cap_chunks = 0, n_chunks = 0;
+    uint32_t merged_chunks = 0;           // interleaved schedules across ranks: log chunks [0, merged_chunks) hold the records of ALL
+                                          // ranks (installed by pcf_round_install), [merged_chunks, n_chunks) this rank's current round
     // normals (append-only records)
     DevBuf n_cell, n_nrm, n_mark;
+    DevBuf upd_cell, upd_nrm;             // normal records of the pass being computed (pcf_update_local), not yet committed
+    uint32_t upd_n = 0, upd_mark = 0;
+    bool upd_open = false;
     uint32_t n_normals = 0;
     std::vector<uint32_t> marks;                       // log slot cursor at each update pass
     std::vector<std::pair<uint32_t, uint32_t>> pending_holder;   // [begin,end) normal records per pass not yet registered
@@ -480,6 +485,13 @@ int prepare_sorted(pcf_ctx* c) {
     return PCF_OK;
 }
 
+// logical cell range [lo, hi) of the x-slab this context works on (whole grid when no slab is set)
+void slab_cells(const pcf_ctx* c, uint32_t& lo, uint32_t& hi) {
+    const uint64_t plane = (uint64_t)c->g.plane_cells;
+    lo = c->slab_hi < 0 ? 0u : (uint32_t)((uint64_t)c->slab_lo * plane);
+    hi = c->slab_hi < 0 ? 0xFFFFFFFFu : (uint32_t)std::min<uint64_t>(c->g.cells, (uint64_t)c->slab_hi * plane);
+}
+
 // scoring of every voxel that has a normal -> sc_a (centroid,count) sc_b (sd,mean_dist) sc_c (sd_dist); nidx map
 int run_scoring(pcf_ctx* c) {
     int rc = prepare_sorted(c);
@@ -493,6 +505,8 @@ int run_scoring(pcf_ctx* c) {
     if ((rc = reserve(c, c->sc_c, (size_t)nn * 4))) return rc;
     LAUNCH(c, k_map_normals, div_up(nn, kBlock), kBlock, (const uint32_t*)c->n_cell.p, nn, c->occ_bits, c->occ_rank, (uint32_t*)c->nidx.p);
     ScoreOut so{(float4*)c->sc_a.p, (float4*)c->sc_b.p, (float*)c->sc_c.p};
+    uint32_t cell_lo, cell_hi;
+    slab_cells(c, cell_lo, cell_hi);
     uint32_t* fault = (uint32_t*)c->total_dev.p + 8;
     CU(cudaMemsetAsync(fault, 0, 32, c->stream));
     // work-balanced voxel -> lane assignment: stable one-pass counting sort of the voxel ids by an 8-bit work key
@@ -508,7 +522,7 @@ int run_scoring(pcf_ctx* c) {
         SortTile* tab = (SortTile*)c->sc_tab.p;
         uint32_t* nt_dev = (uint32_t*)(tab + nt);
         LAUNCH(c, k_score_work, div_up(nn, kBlock), kBlock, (const uint32_t*)c->n_cell.p, (const float4*)c->n_nrm.p, nn, c->g, c->occ_bits,
-               c->occ_rank, (const uint32_t*)c->uv_off.p, (uint32_t*)c->sc_keys.p, (uint32_t*)c->sc_ids.p);
+               c->occ_rank, (const uint32_t*)c->uv_off.p, (uint32_t*)c->sc_keys.p, (uint32_t*)c->sc_ids.p, cell_lo, cell_hi);
         LAUNCH(c, k_sort_flat_tiles, div_up(nt, kBlock), kBlock, nn, tab, nt_dev);
         SortSrc src{};
         src.keys = (const uint32_t*)c->sc_keys.p; src.vals = (const uint32_t*)c->sc_ids.p; src.tab = tab; src.n_tiles_dev = nt_dev;
@@ -522,13 +536,13 @@ int run_scoring(pcf_ctx* c) {
     const bool simple = c->marks.size() == 1 && c->marks[0] == c->n_chunks * (uint32_t)kWChunk && !c->holder;
 #define SCORE_ARGS order, (const uint32_t*)c->n_cell.p, (const float4*)c->n_nrm.p, (const uint32_t*)c->n_mark.p, nn, c->g, c->occ_bits, c->occ_rank, \
                    (const uint32_t*)c->uv_off.p, (const uint32_t*)c->nidx.p, (const float4*)c->sorted.p, (const uint32_t*)c->holder, so,  \
-                   (uint32_t)c->n_points, (const uint32_t*)c->uv_cell.p, fault
+                   (uint32_t)c->n_points, (const uint32_t*)c->uv_cell.p, fault, cell_lo, cell_hi
     // dense buffers (the scans of real surfaces): cooperative kernel; a handful of points per voxel (C5's synthetic sheets):
     // one thread per voxel wastes less
     const bool coop = simple && c->score_coop != 0 && (c->score_coop > 0 || c->n_points >= 8ull * std::max<uint32_t>(c->n_vox, 1u));
     if (coop) LAUNCH(c, k_score_coop, div_up(nn, kCoopWarps * 32), kCoopWarps * 32, order, (const uint32_t*)c->n_cell.p, (const float4*)c->n_nrm.p, nn, c->g,
                      c->occ_bits, c->occ_rank, (const uint32_t*)c->uv_off.p, (const float4*)c->sorted.p, so, (uint32_t)c->n_points,
-                     (const uint32_t*)c->uv_cell.p, fault);
+                     (const uint32_t*)c->uv_cell.p, fault, cell_lo, cell_hi);
     else if (!simple) LAUNCH(c, (k_score<false, 1>), div_up(nn, 128), 128, SCORE_ARGS);
     else if (c->score_unroll >= 4) LAUNCH(c, (k_score<true, 4>), div_up(nn, 128), 128, SCORE_ARGS);
     else if (c->score_unroll >= 2) LAUNCH(c, (k_score<true, 2>), div_up(nn, 128), 128, SCORE_ARGS);
@@ -567,8 +581,10 @@ int extract_impl(pcf_ctx* c, int32_t min_count, pcf_result* out) {
     if (nv && c->n_normals) {
         if ((rc = reserve(c, c->flags, (size_t)nv * 4))) return rc;
         if ((rc = reserve(c, c->slots, (size_t)nv * 4))) return rc;
+        uint32_t cell_lo, cell_hi;
+        slab_cells(c, cell_lo, cell_hi);
         LAUNCH(c, k_extract_flags, div_up(nv, kBlock), kBlock, (const uint32_t*)c->uv_cell.p, nv, (const uint32_t*)c->nidx.p,
-               (const float4*)c->sc_a.p, c->g, min_count, (uint32_t*)c->flags.p);
+               (const float4*)c->sc_a.p, c->g, min_count, (uint32_t*)c->flags.p, cell_lo, cell_hi);
         uint32_t* tot = (uint32_t*)c->total_dev.p;
         if ((rc = scan_u32(c, (uint32_t*)c->flags.p, (uint32_t*)c->slots.p, nv, tot))) return rc;
         if ((rc = read_total(c, tot, &n_out))) return rc;
@@ -620,7 +636,7 @@ void destroy_impl(pcf_ctx* c) {
     DevBuf* bufs[] = {&c->n_cell, &c->n_nrm, &c->n_mark, &c->scan1, &c->scan2, &c->tmpA, &c->tmpB, &c->tmpC, &c->tmpD, &c->hist, &c->sort_tab,
                       &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->sorted, &c->uv_cell, &c->uv_off, &c->nidx, &c->sc_a, &c->sc_b,
                       &c->sc_c, &c->flags, &c->slots, &c->cand, &c->res_dev, &c->total_dev, &c->dense_log, &c->sc_keys, &c->sc_ids,
-                      &c->sc_order, &c->sc_okeys, &c->sc_tab, &c->ex_hist, &c->ex_plan, &c->ex_row};
+                      &c->sc_order, &c->sc_okeys, &c->sc_tab, &c->ex_hist, &c->ex_plan, &c->ex_row, &c->upd_cell, &c->upd_nrm};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     void* raw[] = {c->first_frame, c->holder, c->nrm_bits, c->occ_bits, c->occ_rank, c->vp_table, c->log, c->chunk_count, c->chunk_frame, c->recv_buf};
     for (void* p : raw) if (p) cudaFree(p);
@@ -648,6 +664,8 @@ int reset_grid_state(pcf_ctx* c) {
     CU(cudaMemsetAsync(c->vp_table, 0, (size_t)c->cfg.max_frames * sizeof(float4), c->stream));
     if (c->holder) CU(cudaMemsetAsync(c->holder, 0, c->g.cells * 4, c->stream));
     c->n_chunks = 0;
+    c->merged_chunks = 0;
+    c->upd_open = false;
     c->n_normals = 0;
     c->n_vox = 0;
     c->n_points = 0;
@@ -1064,61 +1082,165 @@ int pcf_count_kept(pcf_ctx* c, uint64_t* kept) {
     return PCF_OK;
 }
 
-int pcf_update(pcf_ctx* c) {
-    if (!c) return PCF_ERR_INVALID;
-    ENTER(c);
-    CU(cudaEventRecord(c->ev_a, c->stream));
+// One update pass in two halves.  update_local: candidates (occupied, no normal yet, inside this context's x-slab) -> 125-probe
+// scan + PCA normal -> the new records compacted into upd_cell / upd_nrm (x-major).  update_commit: append records (the own
+// ones, or the ones gathered from every rank in slab order = x-major order) as this pass and mark the voxels.
+static int update_local_impl(pcf_ctx* c) {
     int rc = flush_holders(c);
     if (rc) return rc;
     if ((rc = build_occupancy(c))) return rc;
     uint32_t mark = c->n_chunks * (uint32_t)kWChunk;   // n_chunks <= 2^24 -> fits (2^32 wraps only at the hard limit)
     if (c->n_chunks >= kMaxChunks) mark = 0xFFFFFFFFu;
-    c->marks.push_back(mark);
-    c->stats.update_passes++;
+    c->upd_mark = mark;
+    c->upd_n = 0;
+    c->upd_open = true;
     uint32_t n_cand = 0;
     uint32_t* tot = (uint32_t*)c->total_dev.p;
-    if (c->n_vox) {
-        if ((rc = reserve(c, c->tmpA, (size_t)c->n_words * 4))) return rc;
-        if ((rc = reserve(c, c->tmpB, (size_t)c->n_words * 4))) return rc;
-        uint32_t* cnt = (uint32_t*)c->tmpA.p;
-        uint32_t* off = (uint32_t*)c->tmpB.p;
-        const uint64_t plane = (uint64_t)c->g.plane_cells;
-        const uint64_t cell_lo = c->slab_hi < 0 ? 0 : (uint64_t)c->slab_lo * plane;
-        const uint64_t cell_hi = c->slab_hi < 0 ? c->g.cells : std::min<uint64_t>(c->g.cells, (uint64_t)c->slab_hi * plane);
-        LAUNCH(c, k_cand_count, div_up(c->n_words, kBlock), kBlock, c->occ_bits, c->nrm_bits, c->n_words, cell_lo, cell_hi, cnt);
-        if ((rc = scan_u32(c, cnt, off, c->n_words, tot))) return rc;
-        if ((rc = read_total(c, tot, &n_cand))) return rc;
-        if (n_cand) {
-            if ((rc = reserve(c, c->cand, (size_t)n_cand * 4))) return rc;
-            if ((rc = reserve(c, c->tmpC, (size_t)n_cand * 16))) return rc;
-            if ((rc = reserve(c, c->tmpD, (size_t)n_cand * 8))) return rc;
-            uint32_t* cand = (uint32_t*)c->cand.p;
-            float4* tnrm = (float4*)c->tmpC.p;
-            uint32_t* flag = (uint32_t*)c->tmpD.p;
-            uint32_t* foff = flag + n_cand;
-            LAUNCH(c, k_cand_list, div_up(c->n_words, kBlock), kBlock, c->occ_bits, c->nrm_bits, c->n_words, cell_lo, cell_hi, off, cand);
-            LAUNCH(c, k_normals, div_up(n_cand, kBlock), kBlock, cand, n_cand, c->g, c->occ_bits, c->first_frame, c->vp_table, tnrm, flag);
-            if ((rc = scan_u32(c, flag, foff, n_cand, tot))) return rc;
-            uint32_t n_new = 0;
-            if ((rc = read_total(c, tot, &n_new))) return rc;
-            if (n_new) {
-                size_t need = (size_t)c->n_normals + n_new;
-                if ((rc = reserve(c, c->n_cell, need * 4, true))) return rc;
-                if ((rc = reserve(c, c->n_nrm, need * 16, true))) return rc;
-                if ((rc = reserve(c, c->n_mark, need * 4, true))) return rc;
-                LAUNCH(c, k_append_normals, div_up(n_cand, kBlock), kBlock, cand, n_cand, tnrm, flag, foff, c->n_normals, mark,
-                       (uint32_t*)c->n_cell.p, (float4*)c->n_nrm.p, (uint32_t*)c->n_mark.p, c->nrm_bits);
-                c->pending_holder.emplace_back(c->n_normals, c->n_normals + n_new);
-                c->n_normals += n_new;
-            }
-        }
+    if (!c->n_vox) return PCF_OK;
+    if ((rc = reserve(c, c->tmpA, (size_t)c->n_words * 4))) return rc;
+    if ((rc = reserve(c, c->tmpB, (size_t)c->n_words * 4))) return rc;
+    uint32_t* cnt = (uint32_t*)c->tmpA.p;
+    uint32_t* off = (uint32_t*)c->tmpB.p;
+    const uint64_t plane = (uint64_t)c->g.plane_cells;
+    const uint64_t cell_lo = c->slab_hi < 0 ? 0 : (uint64_t)c->slab_lo * plane;
+    const uint64_t cell_hi = c->slab_hi < 0 ? c->g.cells : std::min<uint64_t>(c->g.cells, (uint64_t)c->slab_hi * plane);
+    LAUNCH(c, k_cand_count, div_up(c->n_words, kBlock), kBlock, c->occ_bits, c->nrm_bits, c->n_words, cell_lo, cell_hi, cnt);
+    if ((rc = scan_u32(c, cnt, off, c->n_words, tot))) return rc;
+    if ((rc = read_total(c, tot, &n_cand))) return rc;
+    if (!n_cand) return PCF_OK;
+    if ((rc = reserve(c, c->cand, (size_t)n_cand * 4))) return rc;
+    if ((rc = reserve(c, c->tmpC, (size_t)n_cand * 16))) return rc;
+    if ((rc = reserve(c, c->tmpD, (size_t)n_cand * 8))) return rc;
+    uint32_t* cand = (uint32_t*)c->cand.p;
+    float4* tnrm = (float4*)c->tmpC.p;
+    uint32_t* flag = (uint32_t*)c->tmpD.p;
+    uint32_t* foff = flag + n_cand;
+    LAUNCH(c, k_cand_list, div_up(c->n_words, kBlock), kBlock, c->occ_bits, c->nrm_bits, c->n_words, cell_lo, cell_hi, off, cand);
+    LAUNCH(c, k_normals, div_up(n_cand, kBlock), kBlock, cand, n_cand, c->g, c->occ_bits, c->first_frame, c->vp_table, tnrm, flag);
+    if ((rc = scan_u32(c, flag, foff, n_cand, tot))) return rc;
+    uint32_t n_new = 0;
+    if ((rc = read_total(c, tot, &n_new))) return rc;
+    if (n_new) {
+        if ((rc = reserve(c, c->upd_cell, (size_t)n_new * 4))) return rc;
+        if ((rc = reserve(c, c->upd_nrm, (size_t)n_new * 16))) return rc;
+        LAUNCH(c, k_compact_normals, div_up(n_cand, kBlock), kBlock, cand, n_cand, tnrm, flag, foff, (uint32_t*)c->upd_cell.p, (float4*)c->upd_nrm.p);
     }
+    c->upd_n = n_new;
     CU(cudaGetLastError());
+    return PCF_OK;
+}
+
+static int update_commit_impl(pcf_ctx* c, const uint32_t* cells_dev, const float4* nrm_dev, uint32_t n) {
+    if (!c->upd_open) return fail(c, PCF_ERR_INVALID, "pcf_update_commit without pcf_update_local");
+    c->upd_open = false;
+    c->marks.push_back(c->upd_mark);
+    c->stats.update_passes++;
+    if (n) {
+        int rc;
+        size_t need = (size_t)c->n_normals + n;
+        if ((rc = reserve(c, c->n_cell, need * 4, true))) return rc;
+        if ((rc = reserve(c, c->n_nrm, need * 16, true))) return rc;
+        if ((rc = reserve(c, c->n_mark, need * 4, true))) return rc;
+        LAUNCH(c, k_commit_normals, div_up(n, kBlock), kBlock, cells_dev, nrm_dev, n, c->n_normals, c->upd_mark, (uint32_t*)c->n_cell.p,
+               (float4*)c->n_nrm.p, (uint32_t*)c->n_mark.p, c->nrm_bits);
+        CU(cudaGetLastError());
+        c->pending_holder.emplace_back(c->n_normals, c->n_normals + n);
+        c->n_normals += n;
+    }
+    c->stats.normals_found = c->n_normals;
+    c->stats.occupied_voxels = c->n_vox;
+    return PCF_OK;
+}
+
+int pcf_update(pcf_ctx* c) {
+    if (!c) return PCF_ERR_INVALID;
+    ENTER(c);
+    CU(cudaEventRecord(c->ev_a, c->stream));
+    int rc = update_local_impl(c);
+    if (rc) return rc;
+    if ((rc = update_commit_impl(c, (const uint32_t*)c->upd_cell.p, (const float4*)c->upd_nrm.p, c->upd_n))) return rc;
     CU(cudaEventRecord(c->ev_b, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaEventElapsedTime(&c->t_update, c->ev_a, c->ev_b));
-    c->stats.normals_found = c->n_normals;
-    c->stats.occupied_voxels = c->n_vox;
+    return PCF_OK;
+}
+
+int pcf_update_local(pcf_ctx* c, void** cells_dev, void** normals_dev, uint32_t* n_new) {
+    if (!c || !cells_dev || !normals_dev || !n_new) return PCF_ERR_INVALID;
+    ENTER(c);
+    if (c->n_chunks != c->merged_chunks && c->merged_chunks)
+        return fail(c, PCF_ERR_INVALID, "pcf_update_local: this rank's round has not been exchanged (pcf_round_export / pcf_round_install first)");
+    int rc = update_local_impl(c);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    *cells_dev = c->upd_cell.p;
+    *normals_dev = c->upd_nrm.p;
+    *n_new = c->upd_n;
+    return PCF_OK;
+}
+
+int pcf_update_commit(pcf_ctx* c, const void* cells_dev, const void* normals_dev, uint32_t n) {
+    if (!c || (n && (!cells_dev || !normals_dev))) return PCF_ERR_INVALID;
+    CU(cudaSetDevice(c->device));
+    int rc = update_commit_impl(c, (const uint32_t*)cells_dev, (const float4*)normals_dev, n);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    return PCF_OK;
+}
+
+// ---- interleaved schedules across ranks: replicated grid state ---------------------------------------------------------------
+// Between two update passes the frames are split over the ranks; at the update point every rank contributes the records of
+// its frames (pcf_round_export), the caller all-gathers them in rank order (= frame order = arrival order) and every rank
+// installs the SAME merged records (pcf_round_install): log, first-frame grid and occupancy bitmap are then identical on
+// every rank and identical, record for record, to what one GPU fed every frame would hold.  Normal estimation, scoring and
+// extraction are sharded by x-slab (pcf_set_slab + pcf_update_local / pcf_update_commit + pcf_extract).
+int pcf_round_export(pcf_ctx* c, void** records_dev, uint64_t* n_records) {
+    if (!c || !records_dev || !n_records) return PCF_ERR_INVALID;
+    ENTER(c);
+    CU(cudaStreamSynchronize(c->copy_stream));
+    *records_dev = nullptr;
+    *n_records = 0;
+    const uint32_t first = c->merged_chunks, nloc = c->n_chunks - first;
+    uint32_t P = 0;
+    int rc;
+    if (nloc) {
+        if ((rc = reserve(c, c->tmpB, (size_t)nloc * 4))) return rc;
+        uint32_t* off = (uint32_t*)c->tmpB.p;
+        uint32_t* tot = (uint32_t*)c->total_dev.p;
+        if ((rc = scan_u32(c, c->chunk_count + first, off, nloc, tot))) return rc;
+        if ((rc = read_total(c, tot, &P))) return rc;
+        if ((rc = reserve(c, c->dense_log, std::max<size_t>((size_t)P, 1) * sizeof(float4)))) return rc;
+        LAUNCH(c, k_round_export, div_up(nloc, kWarps), kBlock, c->log, c->chunk_count, c->chunk_frame, off, first, c->n_chunks, (float4*)c->dense_log.p);
+        CU(cudaGetLastError());
+    } else if ((rc = reserve(c, c->dense_log, sizeof(float4)))) {
+        return rc;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    *records_dev = c->dense_log.p;
+    *n_records = P;
+    return PCF_OK;
+}
+
+int pcf_round_install(pcf_ctx* c, const void* records_dev, uint64_t n) {
+    if (!c || (!records_dev && n)) return PCF_ERR_INVALID;
+    ENTER(c);
+    const uint32_t chunks = div_up(n, kWChunk);
+    if ((uint64_t)c->merged_chunks + chunks > kMaxChunks) return fail(c, PCF_ERR_CAPACITY, "point log limit reached");
+    c->n_chunks = c->merged_chunks;          // this rank's own chunks of the round are superseded by the merged records (own ones included)
+    int rc = ensure_log(c, std::max<uint32_t>(c->merged_chunks + chunks, 1));
+    if (rc) return rc;
+    if (n) {
+        LAUNCH(c, k_install_records, div_up(n, kBlock), kBlock, (const float4*)records_dev, n, c->g, c->first_frame, c->occ_bits,
+               c->log + (size_t)c->merged_chunks * kWChunk);
+        LAUNCH(c, k_chunk_counts_dense, div_up(chunks, kBlock), kBlock, c->chunk_count + c->merged_chunks, chunks, n);
+        CU(cudaGetLastError());
+    }
+    c->merged_chunks += chunks;
+    c->n_chunks = c->merged_chunks;
+    c->log_installed = true;
+    c->occ_dirty = true;
+    c->sorted_valid = false;
+    CU(cudaStreamSynchronize(c->stream));
     return PCF_OK;
 }
 

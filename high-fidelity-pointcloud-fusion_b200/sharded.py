@@ -12,7 +12,9 @@ scoring and extraction for it, and the slab results concatenated in rank order a
 
 `merge_and_extract` works on a list of in-process ranks (N contexts on one or several GPUs of one process: used by
 the tests) or, with `group=` a torch.distributed process group, on the local rank (one process per GPU, NCCL).
-Interleaved update schedules across ranks are not supported yet (the library refuses, see pcf_log_replace).
+Interleaved update schedules across ranks (an update pass between frames, like the node's 5 s cleanGrid timer) use the
+replicated-state mode at the bottom of this file: records and normal records are all-gathered at every pass, so the grid
+state is identical on all ranks; ingest, normal estimation, scoring and extraction stay sharded.
 """
 from __future__ import annotations
 
@@ -377,3 +379,116 @@ def merge_and_extract(fus, group=None, gather_to=0):
     dist.gather_object(local, parts, dst=gather_to, group=group)
     full = _concat_results(parts) if rank == gather_to else None
     return local, full, timings
+
+
+# ---- interleaved update schedules across ranks: replicated grid state (pcfusion.h "interleaved update schedules") ------------
+def _gather_var(t, group, emulate=None):
+    """All-gather of tensors whose first dimension differs per rank, concatenated in rank order."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(x.item()) for x in sizes]
+    mx = max(max(sizes), 1)
+    pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    out = torch.empty((world * mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    return torch.cat([out[r * mx: r * mx + sizes[r]] for r in range(world)], dim=0).contiguous()
+
+
+class InterleavedSharded:
+    """One process per GPU.  Usage per round (the frames between two update passes, split over the ranks in contiguous
+    sub-blocks with frame_block()):  push this rank's frames into `fus` as usual, then update(frame_lo, frame_hi) with the
+    global frame range of the round; at the end extract()."""
+
+    def __init__(self, fus, group=None):
+        import torch.distributed as dist
+        self.fus, self.group = fus, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.dev = torch.device("cuda", fus.device_index)
+        self.bounds = None
+
+    def exchange_round(self, frame_lo, frame_hi):
+        import torch.distributed as dist
+        p, n = self.fus.round_export()
+        mine = _as_tensor(p, (max(n, 1), 4), "<f4", self.dev)[:n]
+        merged = _gather_var(mine, self.group)
+        vp, nf = self.fus.viewpoint_table()
+        dist.all_reduce(_as_tensor(vp, (nf, 4), "<f4", self.dev)[frame_lo:frame_hi], group=self.group)   # rows of this round only
+        torch.cuda.synchronize(self.dev)
+        self.fus.round_install(merged, merged.shape[0])
+
+    def _slabs(self):
+        self.bounds = slab_bounds_from_points(self.fus.plane_point_counts(), self.world)   # the log is replicated: same bounds everywhere
+        self.fus.set_slab(self.bounds[self.rank], self.bounds[self.rank + 1])
+
+    def update(self, frame_lo, frame_hi):
+        self.exchange_round(frame_lo, frame_hi)
+        self._slabs()
+        pc, pn, n = self.fus.update_local()
+        cells = _gather_var(_as_tensor(pc, (max(n, 1),), "<i4", self.dev)[:n], self.group)
+        nrms = _gather_var(_as_tensor(pn, (max(n, 1), 4), "<f4", self.dev)[:n], self.group)
+        torch.cuda.synchronize(self.dev)
+        self.fus.update_commit(cells, nrms, cells.shape[0])
+
+    def extract(self, gather_to=0):
+        import torch.distributed as dist
+        if self.bounds is None:
+            self._slabs()
+        local = self.fus.extract()
+        parts = [None] * self.world if self.rank == gather_to else None
+        dist.gather_object(local, parts, dst=gather_to, group=self.group)
+        return local, (_concat_results(parts) if self.rank == gather_to else None)
+
+
+def interleaved_local(ranks, scene_frames, update_every):
+    """In-process emulation of InterleavedSharded on a list of contexts (tests): frames = [(pts, pose)], an update pass after
+    every `update_every` frames (and a final one); the gathers are plain tensor concatenations between the contexts."""
+    world = len(ranks)
+    devs = [torch.device("cuda", f.device_index) for f in ranks]
+    n = len(scene_frames)
+    bounds = None
+
+    def do_update(lo, hi):
+        nonlocal bounds
+        recs, vps = [], None
+        for f, d in zip(ranks, devs):
+            p, k = f.round_export()
+            recs.append(_as_tensor(p, (max(k, 1), 4), "<f4", d)[:k].to(devs[0]))
+            vp, nf = f.viewpoint_table()
+            v = _as_tensor(vp, (nf, 4), "<f4", d)[lo:hi].to(devs[0])
+            vps = v.clone() if vps is None else vps + v
+        merged = torch.cat(recs, dim=0).contiguous()
+        for f, d in zip(ranks, devs):
+            vp, nf = f.viewpoint_table()
+            _as_tensor(vp, (nf, 4), "<f4", d)[lo:hi].copy_(vps.to(d))
+            m = merged.to(d)
+            torch.cuda.synchronize(d)
+            f.round_install(m, m.shape[0])
+        bounds = slab_bounds_from_points(ranks[0].plane_point_counts(), world)
+        cells, nrms = [], []
+        for r, (f, d) in enumerate(zip(ranks, devs)):
+            f.set_slab(bounds[r], bounds[r + 1])
+            pc, pn, k = f.update_local()
+            cells.append(_as_tensor(pc, (max(k, 1),), "<i4", d)[:k].to(devs[0]).clone())
+            nrms.append(_as_tensor(pn, (max(k, 1), 4), "<f4", d)[:k].to(devs[0]).clone())
+        cells, nrms = torch.cat(cells).contiguous(), torch.cat(nrms, dim=0).contiguous()
+        for f, d in zip(ranks, devs):
+            cc, nn_ = cells.to(d), nrms.to(d)
+            torch.cuda.synchronize(d)
+            f.update_commit(cc, nn_, cc.shape[0])
+
+    start = 0
+    while start < n:
+        stop = min(start + (update_every or n), n)
+        for r, f in enumerate(ranks):
+            lo, hi = frame_block(stop - start, r, world)
+            for i in range(start + lo, start + hi):
+                f.push_frame(scene_frames[i][0], scene_frames[i][1], i)
+        do_update(start, stop)
+        start = stop
+    if update_every and n % update_every == 0:
+        do_update(n, n)                                   # the final pass of run_schedule() (no new frames)
+    return _concat_results([f.extract() for f in ranks])

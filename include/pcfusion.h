@@ -255,6 +255,26 @@ int pcf_get_viewpoints(pcf_ctx* ctx, float* host4, uint32_t first, uint32_t coun
 int pcf_set_viewpoints(pcf_ctx* ctx, const float* host4, uint32_t first, uint32_t count);
 int pcf_enable_peer_access(pcf_ctx* ctx, int32_t peer_device);
 
+/* ---- interleaved update schedules across ranks: replicated grid state, sharded ingest / normals / scoring / extraction ---------
+ * (the live node's cleanGrid pass every 5 s, node.cpp:301-325, combined with frame sharding).  Between two update passes the
+ * frames are split over the ranks in contiguous sub-blocks.  At an update point:
+ *   pcf_round_export    this rank's records since the last round, (x, y, z, frame_idx) in arrival order, device memory;
+ *   [the caller all-gathers the records in rank order = frame order = arrival order, and sums the viewpoint rows of the round]
+ *   pcf_round_install   every rank appends the SAME gathered records to its log (and applies them to the first-frame grid and the
+ *                       occupancy bitmap): the grid state is now identical on all ranks and, record for record, the one a single
+ *                       GPU fed every frame would hold (same arrival order, same cursor at the pass);
+ *   pcf_set_slab + pcf_update_local   neighbour scan + PCA normals of the candidates in this rank's x-slab (any partition works,
+ *                       it may change from pass to pass: the state is replicated), records NOT committed;
+ *   [the caller all-gathers (cell, normal) in slab order = x-major order]
+ *   pcf_update_commit   every rank appends the same records as this pass; holders / dependants (OG.hpp:417,443-449) follow from
+ *                       the replicated records exactly as on one GPU.
+ * pcf_extract with a slab set scores and extracts only that slab; the slabs concatenated in rank order are the x-major scan.
+ * pcf_update == pcf_update_local + pcf_update_commit of the own records. */
+int pcf_round_export(pcf_ctx* ctx, void** records_dev, uint64_t* n_records);
+int pcf_round_install(pcf_ctx* ctx, const void* records_dev, uint64_t n_records);
+int pcf_update_local(pcf_ctx* ctx, void** cells_dev /* uint32 */, void** normals_dev /* float4 */, uint32_t* n_new);
+int pcf_update_commit(pcf_ctx* ctx, const void* cells_dev, const void* normals_dev, uint32_t n);
+
 /* ---- known-answer hooks: run ONE device function over an array (tests bit-compare with the oracle) ---- */
 int pcf_kat_transform_voxel(pcf_ctx* ctx, const float* pts_host, uint32_t n, uint32_t stride_floats,
                             const double pose[16], float* world_xyz, int32_t* ijk, uint8_t* kept);

@@ -411,3 +411,26 @@ def test_randomised_scenes_and_schedules(pcf, oracle, seed):
     assert_same(fus.state(), og.state(), STATE_FIELDS, f"fuzz {seed} state.")
     assert_result_parity(fus.extract(), og.download(), f"fuzz {seed} result.")
     fus.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("update_every", [1, 2, 4, None])
+def test_interleaved_schedule_across_ranks_byte_identical(pcf, oracle, small, world, update_every):
+    """an update pass between frames (the node's cleanGrid timer, node.cpp:301-325) combined with frame
+    sharding.  Replicated-state mode (pcf_round_export / _install, pcf_update_local / _commit): the frames of every round are
+    split over the ranks, records and normal records are gathered at every pass; the slabs' extractions concatenated in rank
+    order equal the oracle (and so one GPU) bit for bit -- incremental dependants scoring (OG.hpp:244-277), unbuffered points
+    (OG.hpp:210-216) and last-registrant holders (OG.hpp:443-449) included."""
+    import importlib
+    sh = importlib.import_module(pcf.__name__ + ".sharded")
+    g = small.grid
+    frames = [small.frame(i) for i in range(small.n_frames)]
+    og = oracle.OracleGrid(g.box, g.res)
+    run_schedule(og, small, update_every)
+    want = og.download()
+    assert len(want) > 1000
+    ranks = [pcf.Fusion(g.box, g.res) for _ in range(world)]
+    got = sh.interleaved_local(ranks, frames, update_every)
+    assert_result_parity(got, want, f"interleaved x{world} every {update_every}: ")
+    for f in ranks:
+        f.close()
