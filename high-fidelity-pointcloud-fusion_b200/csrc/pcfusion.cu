@@ -1226,9 +1226,12 @@ int pcf_round_install(pcf_ctx* c, const void* records_dev, uint64_t n) {
     ENTER(c);
     const uint32_t chunks = div_up(n, kWChunk);
     if ((uint64_t)c->merged_chunks + chunks > kMaxChunks) return fail(c, PCF_ERR_CAPACITY, "point log limit reached");
-    c->n_chunks = c->merged_chunks;          // this rank's own chunks of the round are superseded by the merged records (own ones included)
-    int rc = ensure_log(c, std::max<uint32_t>(c->merged_chunks + chunks, 1));
+    // holders of the previous pass are registered against the occupancy AS OF that pass (OG.hpp:443-449): a rank that pushed no
+    // frame of its own in this round has not done it yet, and the records installed below change the occupancy
+    int rc = flush_holders(c);
     if (rc) return rc;
+    c->n_chunks = c->merged_chunks;          // this rank's own chunks of the round are superseded by the merged records (own ones included)
+    if ((rc = ensure_log(c, std::max<uint32_t>(c->merged_chunks + chunks, 1)))) return rc;
     if (n) {
         LAUNCH(c, k_install_records, div_up(n, kBlock), kBlock, (const float4*)records_dev, n, c->g, c->first_frame, c->occ_bits,
                c->log + (size_t)c->merged_chunks * kWChunk);
