@@ -183,11 +183,13 @@ def _ptr(a):
     return a.data_ptr()   # torch tensor
 
 
-def kat_clip_pack(data, rows, cols, point_step, row_step, x_offset, lo, hi, isa=-1):
+def kat_clip_pack(data, rows, cols, point_step, row_step, x_offset, lo, hi, isa=-1, misalign=False):
     """The staging pool's clip-and-pack on a raw message buffer (host only: works without a GPU).  Returns (xyz [m, 3], isa used)."""
     lib = load_library()
     data = np.ascontiguousarray(data, np.uint8)
-    out = np.empty(3 * rows * cols + 16, np.float32)
+    raw = np.empty(3 * rows * cols + 16 + 32, np.float32)
+    shift = (-raw.ctypes.data // 4) % 16 + (1 if misalign else 0)    # 64-byte aligned output (the non-temporal path) or deliberately not
+    out = raw[shift:]
     m = C.c_uint32()
     used = lib.pcf_kat_clip_pack(data.ctypes.data, rows, cols, point_step, row_step, x_offset, lo, hi, isa, out.ctypes.data, C.byref(m))
     if used < 0:

@@ -21,7 +21,10 @@ int main(int argc, char** argv) {
             float* p = &src[f][(size_t)i * 4];
             p[0] = hit ? 0.001f * u : NAN; p[1] = hit ? 0.001f * v : NAN; p[2] = hit ? 0.3f + 1e-4f * (i % 1000) : NAN; p[3] = 0.f;
         }
-    std::vector<std::vector<float>> dst(threads, std::vector<float>((size_t)(n + 4) * 3));
+    // every thread cycles through 8 destination slots (like the pinned slot ring: the packed clouds do not stay in the cache)
+    const size_t slot_floats = ((size_t)n * 3 + 16 + 15) / 16 * 16;
+    std::vector<float*> dst(threads);
+    for (int t = 0; t < threads; t++) dst[t] = static_cast<float*>(aligned_alloc(4096, 8 * slot_floats * sizeof(float)));
     for (int rep = 0; rep < 3; rep++) {
         auto t0 = std::chrono::steady_clock::now();
         std::vector<std::thread> pool;
@@ -34,7 +37,7 @@ int main(int argc, char** argv) {
                         pcf::StageJob j;
                         j.data = reinterpret_cast<const uint8_t*>(src[f].data());
                         j.rows = 1; j.cols = n; j.point_step = 16; j.x_offset = 0;
-                        kept[t] += pcf::clip_pack(j, 0.28f, 0.6f, dst[t].data());
+                        kept[t] += pcf::clip_pack(j, 0.28f, 0.6f, dst[t] + (size_t)((f / threads) & 7) * slot_floats);
                     }
             });
         for (auto& th : pool) th.join();
