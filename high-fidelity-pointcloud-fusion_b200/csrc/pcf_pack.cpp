@@ -58,44 +58,9 @@ __attribute__((target("avx512f,avx512vl,popcnt"))) uint32_t pack_row_avx512(cons
     return k;
 }
 
-// Same loop with NON-TEMPORAL output.  The packed cloud is written once and next read by the copy engine, never by this
-// core: ordinary stores would first read every destination line into the cache (read-for-ownership) and write it back
-// later -- on a host whose memory bandwidth bounds the staging pool that is a fifth of the traffic.  The compressed lanes
-// are collected in a 64-byte-aligned line buffer and every completed line is streamed out (VMOVNTPS).  Flat float4 clouds
-// with a 64-byte-aligned destination only; `k` must be 0 on entry.
-template <int P>
-__attribute__((target("avx512f,avx512vl,popcnt"))) uint32_t pack_flat_avx512_nt(const uint8_t* p, uint32_t cols, uint32_t xo, float lo, float hi, float* out) {
-    constexpr int PPV = 16 / P;
-    const __m512 vlo = _mm512_set1_ps(lo), vhi = _mm512_set1_ps(hi);
-    __mmask16 zmask = 0;
-    for (int j = 0; j < PPV; j++) zmask |= (__mmask16)(1u << (j * P + xo + 2));
-    const float* src = reinterpret_cast<const float*>(p);
-    alignas(64) float buf[48];
-    size_t base = 0;                 // floats already streamed out (multiple of 16)
-    uint32_t fill = 0;               // floats waiting in buf
-    uint32_t c = 0, k = 0;
-    for (; c + PPV <= cols; c += PPV, src += 16) {
-        _mm_prefetch(reinterpret_cast<const char*>(src) + kPrefetchAhead, _MM_HINT_T0);
-        __m512 v = _mm512_loadu_ps(src);
-        __mmask16 m = _mm512_cmp_ps_mask(v, vlo, _CMP_GT_OQ) & _mm512_cmp_ps_mask(v, vhi, _CMP_LT_OQ) & zmask;
-        __mmask16 m3 = (__mmask16)((uint32_t)(m >> 2) * 7u);
-        _mm512_storeu_ps(buf + fill, _mm512_maskz_compress_ps(m3, v));
-        const uint32_t n = (uint32_t)_mm_popcnt_u32(m);
-        k += n;
-        fill += 3 * n;
-        if (fill >= 16) {            // at most one line completes per step (a step adds <= 12 floats)
-            _mm512_stream_ps(out + base, _mm512_load_ps(buf));
-            _mm512_store_ps(buf, _mm512_load_ps(buf + 16));
-            base += 16;
-            fill -= 16;
-        }
-    }
-    for (uint32_t i = 0; i < fill; i++) out[base + i] = buf[i];
-    _mm_sfence();                    // the streamed lines are globally visible before the cloud is handed to the copy engine
-    if (c < cols) k = pack_row_scalar(reinterpret_cast<const uint8_t*>(src) + xo * 4, cols - c, P * 4, lo, hi, out, k);
-    return k;
-}
-
+// (A variant with non-temporal output -- compressed lanes collected in an aligned line buffer and streamed out with VMOVNTPS,
+//  to spare the read-for-ownership of every destination line -- was measured on the GPU host: 5.7-5.9 vs 6.4 G points/s for
+//  the loop alone, no difference end to end.  Not kept.)
 // float4 points, two per 256-bit vector
 __attribute__((target("avx2,popcnt"))) uint32_t pack_row_avx2(const uint8_t* p, uint32_t cols, float lo, float hi, float* out, uint32_t k) {
     alignas(32) static const int32_t kIdx[4][8] = {{0, 1, 2, 4, 5, 6, 3, 7}, {0, 1, 2, 4, 5, 6, 3, 7}, {4, 5, 6, 0, 1, 2, 3, 7}, {0, 1, 2, 4, 5, 6, 3, 7}};
@@ -143,10 +108,6 @@ uint32_t clip_pack_with(int isa, const StageJob& j, float clip_lo, float clip_hi
             isa = clip_pack_isa();
     }
     uint32_t k = 0;
-    static const bool nt = std::getenv("PCF_PACK_NT") ? std::atoi(std::getenv("PCF_PACK_NT")) != 0 : true;
-    if (isa == 2 && nt && j.rows == 1 && ((uintptr_t)out & 63u) == 0 && j.x_offset / 4 <= 1 && j.point_step == 16) {
-        k = pack_flat_avx512_nt<4>(j.data, j.cols, j.x_offset / 4, clip_lo, clip_hi, out);
-    } else
     for (uint32_t r = 0; r < j.rows; r++) {
         const uint8_t* row = j.data + (size_t)r * j.row_step;
         const uint32_t xo = j.x_offset / 4;

@@ -47,7 +47,7 @@ def test_clip_pack_all_implementations_agree_with_the_definition(point_step, x_o
     z = xyz[:, 2].astype(np.float64)
     want = xyz[(z > 0.28) & (z < 0.6)]                                  # node.cpp:251 on doubles; NaN fails
     got = {}
-    for isa in (0, 1, 2, -1, "2-unaligned"):     # a 64-byte aligned output takes the non-temporal AVX-512 loop, a misaligned one the plain loop
+    for isa in (0, 1, 2, -1, "2-unaligned"):     # 64-byte aligned and deliberately misaligned output buffers
         mis = isa == "2-unaligned"
         out, used = pcf.kat_clip_pack(msg, rows, cols, point_step, row_step, x_offset, lo, hi, 2 if mis else isa, misalign=mis)
         assert len(out) % 4 == 0 and 0 <= len(out) - len(want) < 4
