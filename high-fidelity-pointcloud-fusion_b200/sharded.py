@@ -434,10 +434,13 @@ class InterleavedSharded:
         self.fus.update_commit(cells, nrms, cells.shape[0])
 
     def extract(self, gather_to=0):
+        """(this rank's slab result, merged result on rank `gather_to`); gather_to=None keeps every slab where it is."""
         import torch.distributed as dist
         if self.bounds is None:
             self._slabs()
         local = self.fus.extract()
+        if gather_to is None:
+            return local, None
         parts = [None] * self.world if self.rank == gather_to else None
         dist.gather_object(local, parts, dst=gather_to, group=self.group)
         return local, (_concat_results(parts) if self.rank == gather_to else None)
