@@ -24,7 +24,9 @@ for variant in os.environ.get("PROF_VARIANTS", "").split(";"):
             fus.push_frames_device(dev[b], min(B, n - b), scene.points_per_frame, 4, poses[b:b + B], b)
         fus.update()
         nv = fus.extract_raw()
-        print("variant", variant or "-", "rep", rep, "voxels", nv, fus.timings(), flush=True)
+        st = fus.stats()
+        print("variant", variant or "-", "rep", rep, "voxels", nv, "kept", st["points_kept"], "occupied", st["occupied_voxels"], "normals", st["normals_found"],
+              fus.timings(), flush=True)
         fus.clear()
     fus.close()
     os.environ.clear(); os.environ.update(saved)
