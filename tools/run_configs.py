@@ -43,6 +43,7 @@ def run_scene(name, scene, n_frames, batch, update_every=0, oracle=False, frames
 
 
 _CTX = {}
+_ORACLE_KIND = "oracle"    # --oracle-kind ref_ordered: the reference's own header (dense grid: 16 GB at 1000^3) instead of the restatement
 _PREMUL = None     # optional fixed transform applied to every pose after the clouds were generated (layout experiments)
 
 
@@ -60,7 +61,7 @@ def _run_scene(name, scene, n_frames, batch, update_every, oracle, frames_per_ge
     og = None
     if oracle:
         import oracle as O
-        og = O.OracleGrid(g.box, g.res, g.clip_zmin, g.clip_zmax)
+        og = O.OracleGrid(g.box, g.res, g.clip_zmin, g.clip_zmax, kind=_ORACLE_KIND)
     t_cpu = 0.0
     done = 0
     while done < n_frames:
@@ -115,6 +116,10 @@ def _run_scene(name, scene, n_frames, batch, update_every, oracle, frames_per_ge
         from helpers import RESULT_FIELDS, bits_equal
         t0 = time.perf_counter(); og.update(); want = og.download(); t_proc = time.perf_counter() - t0
         line["oracle_bit_exact"] = all(bits_equal(getattr(res, f), getattr(want, f)) for f in RESULT_FIELDS)
+        line["oracle_kind"] = _ORACLE_KIND
+        line["oracle_voxels"] = len(want)
+        line["result_checksums"] = bench.checksums(res)
+        line["oracle_checksums"] = bench.checksums(want)
         line["cpu_points_per_s"] = n_frames * npf / t_cpu
         line["cpu_process_ms"] = t_proc * 1e3
         og.close()
@@ -164,10 +169,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("configs", nargs="*", default=["C1", "C2"])
     ap.add_argument("--oracle", action="store_true")
+    ap.add_argument("--oracle-kind", default="oracle", choices=["oracle", "ref_ordered", "ref"])
     ap.add_argument("--c3-frames", type=int, default=1000)
     ap.add_argument("--c5-sheets", type=int, default=100)
     ap.add_argument("--c5-side", type=int, default=1000)
     a = ap.parse_args()
+    global _ORACLE_KIND
+    _ORACLE_KIND = a.oracle_kind
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     for c in a.configs:
         if c == "C1":
@@ -175,9 +183,11 @@ def main():
         elif c == "C2":
             line = run_scene("C2 turntable200", synth.sphere_turntable(200, rings=2), 200, 200, oracle=a.oracle)
         elif c == "C3":
-            line = run_scene(f"C3 sweep{a.c3_frames}", synth.plate_sweep(a.c3_frames), a.c3_frames, 250, oracle=False, frames_per_gen=250)
+            line = run_scene(f"C3 sweep{a.c3_frames}", synth.plate_sweep(a.c3_frames), a.c3_frames, 250, oracle=a.oracle, frames_per_gen=250,
+                             passes=1 if a.oracle else 2)
         elif c == "C4":
-            line = run_scene("C4 hires50", synth.hires_sphere(50), 50, 10, update_every=10, oracle=False, frames_per_gen=10)
+            line = run_scene("C4 hires50", synth.hires_sphere(50), 50, 10, update_every=10, oracle=a.oracle, frames_per_gen=10,
+                             passes=1 if a.oracle else 2)
         elif c.startswith("C3x"):       # C3x200: C3 with the fusion frame rotated so that the plate lies in the y-z plane
             nfr = int(c[3:])            # (layout experiment: the same points land in few x-planes of the x-major grid)
             global _PREMUL
