@@ -723,7 +723,7 @@ void pcf_default_config(pcf_config* cfg) {
     cfg->max_frames = 1u << 16;
     cfg->log_capacity_hint = 0;
     cfg->stage_threads = 0;                                   // auto
-    cfg->stage_raw_lanes = 0;                                 // off
+    cfg->stage_raw_lanes = 0;                                 // auto
 }
 
 int pcf_create(const pcf_config* cfg, pcf_ctx** out) {
@@ -932,7 +932,11 @@ static int ensure_stager(pcf_ctx* c) {
     h.push = [c](int s, const float* xyz, uint32_t n_staged, uint32_t n_offered, const double* pose, uint32_t frame_idx) {
         return push_host_cloud_impl(c, xyz, (size_t)n_staged * 12, 0, n_staged, 3, nullptr, pose, nullptr, frame_idx, n_offered, c->slot_ev[s]);
     };
-    int raw_lanes = std::max(c->cfg.stage_raw_lanes, 0);
+    // raw lanes: measured harmful where the packers saturate the host's memory bandwidth (16 vCPUs, 12 packers: 6.0 -> 5.4 G
+    // points/s) and useful where cores are scarce (8 GPUs on 32 vCPUs, 3 packers per GPU: the link would idle behind them).
+    // Auto: none with 8 or more packers, else 8 (every lane holds one cloud in flight; a lane waits for its own copy, so
+    // the link is never oversubscribed).
+    int raw_lanes = c->cfg.stage_raw_lanes == 0 ? (threads >= 8 ? 0 : 8) : std::max(c->cfg.stage_raw_lanes, 0);
     if (const char* e = getenv("PCF_RAW_LANES")) raw_lanes = std::max(atoi(e), 0);
     h.raw_ok = [](const StageJob& j) {
         if (j.x_offset != 0 || (j.point_step != 16 && j.point_step != 12) || ((uintptr_t)j.data & 15u)) return false;

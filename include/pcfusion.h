@@ -58,9 +58,9 @@ typedef struct {
     int32_t stage_threads;       /* host staging threads of pcf_submit_* (the reference has ONE addPoints thread,
                                     node.cpp:166,218); 0 = min(16, 3/4 of the hardware threads); env PCF_STAGE_THREADS overrides */
     int32_t stage_raw_lanes;     /* extra threads that upload pinned float4 / xyz clouds UNSTAGED while clouds pile up behind the
-                                    packers, using the PCIe time the staged copies leave free; 0 = none (default: on hosts whose
-                                    memory bandwidth bounds the packers the extra DMA traffic costs more than it brings, see
-                                    DESIGN.md); env PCF_RAW_LANES overrides */
+                                    packers, using the PCIe time the staged copies leave free.  0 = auto: none when there are 8 or
+                                    more packers (they saturate the host's memory bandwidth; raw DMA traffic then costs more than
+                                    it brings), 8 on core-starved hosts; < 0 = none; env PCF_RAW_LANES overrides */
 } pcf_config;
 
 /* Extraction output, structure of arrays, x-major voxel order = the reference's scan order

@@ -3,7 +3,7 @@ set -x
 cd $GRAFT_REPO_ROOT
 N=${1:-8}; tag=${2:-r}
 mkdir -p gpurun_out
-for lanes in 2 4; do
+for lanes in 8; do
 PCF_RAW_LANES=$lanes timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 --no-c3 2>gpurun_out/bench_n${N}_lanes${lanes}_$tag.err | grep "^{" > gpurun_out/bench_n${N}_lanes${lanes}_$tag.json
 python - <<PY
 import json
