@@ -19,7 +19,7 @@ namespace {
 // buffers x latency); prefetching well ahead, across 4 KB page boundaries where the hardware streamer stops, keeps more
 // lines in flight per core
 #ifndef PCF_PREFETCH_AHEAD
-#define PCF_PREFETCH_AHEAD 2048
+#define PCF_PREFETCH_AHEAD 4096
 #endif
 constexpr int kPrefetchAhead = PCF_PREFETCH_AHEAD;
 
