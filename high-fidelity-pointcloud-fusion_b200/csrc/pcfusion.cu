@@ -44,6 +44,7 @@ struct pcf_ctx {
     int ctas_per_sm = kBulkMinBlocks;     // persistent CTAs per SM of the bulk kernel
     bool trace = false;                   // PCF_TRACE=1
     bool use_bulk = true;                 // PCF_INGEST=generic forces the plain-load kernel (A/B measurements)
+    bool ingest_bits = true;              // PCF_INGEST_BITS=0: the ingest kernels leave the occupancy bitmap alone and it is rebuilt by a grid sweep (A/B)
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     std::string err;
     bool started = false;
@@ -340,6 +341,10 @@ int flush_holders(pcf_ctx* c) {
 
 // one launch over `nf` equally sized clouds resident in device memory.  Batch = IngestBatch (up to 256 frames, 24 KB of
 // kernel parameters) or IngestBatch1 (one frame, 144 bytes: the per-frame host path launches 200 times per step).
+inline uint32_t* ingest_occ(pcf_ctx* c) {
+    if (!c->ingest_bits) { c->occ_from_grid = true; return nullptr; }
+    return c->occ_bits;
+}
 // stride: floats per point; 0 = organized PointCloud2 layout described by `rows` (generic kernel only)
 template <class Batch>
 int launch_ingest_t(pcf_ctx* c, const float* pts_dev, uint64_t frame_stride, uint32_t n, uint32_t nf, uint32_t stride,
@@ -363,7 +368,7 @@ int launch_ingest_t(pcf_ctx* c, const float* pts_dev, uint64_t frame_stride, uin
     if (rows) rl = *rows;
     if (explicit_vp) {       // pcf_add_points: cloud already in the fusion frame
         dim3 grid(div_up(chunks, kWarps), nf, 1);
-        LAUNCH(c, (k_ingest<0, true, Batch>), grid, kBlock, b, rl, g, c->first_frame, c->occ_bits, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
+        LAUNCH(c, (k_ingest<0, true, Batch>), grid, kBlock, b, rl, g, c->first_frame, ingest_occ(c), c->log, c->chunk_count, c->chunk_frame, c->vp_table);
         CU(cudaGetLastError());
         c->n_chunks += chunks * nf;
         return PCF_OK;
@@ -373,14 +378,14 @@ int launch_ingest_t(pcf_ctx* c, const float* pts_dev, uint64_t frame_stride, uin
     const uint32_t total = chunks * nf;
     const uint32_t grid_bulk = std::min<uint32_t>((uint32_t)(c->sm_count * c->ctas_per_sm), div_up(total, kWarps));
     if (c->use_bulk && aligned && stride == 4 && !rows) {
-        LAUNCH_SMEM(c, (k_ingest_bulk<16, kBulkMinBlocks, kBulkRounds, 1, Batch>), grid_bulk, kBlock, kWarps * kWChunk * 16, b, g, c->first_frame, c->occ_bits, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
+        LAUNCH_SMEM(c, (k_ingest_bulk<16, kBulkMinBlocks, kBulkRounds, 1, Batch>), grid_bulk, kBlock, kWarps * kWChunk * 16, b, g, c->first_frame, ingest_occ(c), c->log, c->chunk_count, c->chunk_frame, c->vp_table);
     } else if (c->use_bulk && aligned && stride == 3 && n % 4 == 0 && !rows) {
-        LAUNCH_SMEM(c, (k_ingest_bulk<12, kBulkMinBlocks, kBulkRounds, 1, Batch>), grid_bulk, kBlock, kWarps * kWChunk * 12, b, g, c->first_frame, c->occ_bits, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
+        LAUNCH_SMEM(c, (k_ingest_bulk<12, kBulkMinBlocks, kBulkRounds, 1, Batch>), grid_bulk, kBlock, kWarps * kWChunk * 12, b, g, c->first_frame, ingest_occ(c), c->log, c->chunk_count, c->chunk_frame, c->vp_table);
     } else {
         dim3 grid(div_up(chunks, kWarps), nf, 1);
-        if (stride == 4 && !rows) LAUNCH(c, (k_ingest<4, false, Batch>), grid, kBlock, b, rl, g, c->first_frame, c->occ_bits, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
-        else if (stride == 3 && !rows) LAUNCH(c, (k_ingest<3, false, Batch>), grid, kBlock, b, rl, g, c->first_frame, c->occ_bits, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
-        else LAUNCH(c, (k_ingest<0, false, Batch>), grid, kBlock, b, rl, g, c->first_frame, c->occ_bits, c->log, c->chunk_count, c->chunk_frame, c->vp_table);
+        if (stride == 4 && !rows) LAUNCH(c, (k_ingest<4, false, Batch>), grid, kBlock, b, rl, g, c->first_frame, ingest_occ(c), c->log, c->chunk_count, c->chunk_frame, c->vp_table);
+        else if (stride == 3 && !rows) LAUNCH(c, (k_ingest<3, false, Batch>), grid, kBlock, b, rl, g, c->first_frame, ingest_occ(c), c->log, c->chunk_count, c->chunk_frame, c->vp_table);
+        else LAUNCH(c, (k_ingest<0, false, Batch>), grid, kBlock, b, rl, g, c->first_frame, ingest_occ(c), c->log, c->chunk_count, c->chunk_frame, c->vp_table);
     }
     CU(cudaGetLastError());
     c->n_chunks += chunks * nf;
@@ -756,6 +761,8 @@ int pcf_create(const pcf_config* cfg, pcf_ctx** out) {
         c->trace = t && atoi(t) > 0;
         const char* e = getenv("PCF_INGEST");
         c->use_bulk = !(e && strcmp(e, "generic") == 0);
+        const char* ib = getenv("PCF_INGEST_BITS");
+        if (ib) c->ingest_bits = atoi(ib) != 0;
         const char* u = getenv("PCF_SCORE_UNR");
         if (u && atoi(u) > 0) c->score_unroll = atoi(u);
         const char* bl = getenv("PCF_SCORE_BALANCE");
