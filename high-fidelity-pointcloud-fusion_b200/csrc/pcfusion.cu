@@ -443,21 +443,23 @@ int prepare_sorted(pcf_ctx* c) {
 
     int bits = 1;
     while ((1ull << bits) < c->g.cells) bits++;
-    // pass M: the top digit, straight from the log; then local LSD passes over the remaining low bits inside each bucket
+    // pass M: the top digit of the CELL, straight from the log, writing the voxel's compact id as the key; then local LSD
+    // passes over (id - first id of the bucket) inside each bucket: as many bits as the fullest bucket has voxels
     const int msd_bits = std::min(8, bits), rem = bits - msd_bits;
-    const int lp = (rem + 7) / 8, per = lp ? (rem + lp - 1) / lp : 0;
     const uint32_t tiles_m = div_up(c->n_chunks, kWarps);
     const uint32_t tiles_max = div_up(P, kChunk) + 256;              // every bucket may end with a partial tile
     if ((rc = reserve(c, c->hist, (size_t)256 * std::max(tiles_m, tiles_max) * 4))) return rc;
-    if ((rc = reserve(c, c->sort_tab, (size_t)tiles_max * sizeof(SortTile) + 2 * 257 * 4))) return rc;
+    if ((rc = reserve(c, c->sort_tab, (size_t)tiles_max * sizeof(SortTile) + (257 + 258 + 257) * 4))) return rc;
     uint32_t* hist = (uint32_t*)c->hist.p;
     SortTile* tab = (SortTile*)c->sort_tab.p;
     uint32_t* bucket_start = (uint32_t*)(tab + tiles_max);
     uint32_t* tile_base = bucket_start + 257;
+    uint32_t* bucket_rank0 = tile_base + 258;
     uint32_t *kin = nullptr, *vin = nullptr, *kout = (uint32_t*)c->keysA.p, *vout = (uint32_t*)c->valsA.p;
     {
         SortSrc src{};
         src.log = c->log; src.chunk_count = c->chunk_count; src.n_chunks = c->n_chunks; src.n_tiles = tiles_m;
+        src.occ_bits = c->occ_bits; src.occ_rank = c->occ_rank;
         const uint32_t mask = (1u << msd_bits) - 1;
         LAUNCH(c, k_sort_hist<true>, tiles_m, kBlock, src, (uint32_t)rem, mask, hist);
         if ((rc = scan_u32(c, hist, hist, (uint64_t)256 * tiles_m, nullptr))) return rc;
@@ -465,15 +467,22 @@ int prepare_sorted(pcf_ctx* c) {
         kin = kout; vin = vout;
         kout = (uint32_t*)c->keysB.p; vout = (uint32_t*)c->valsB.p;
     }
+    LAUNCH(c, k_sort_bucket_tiles, 1, 256, (const uint32_t*)hist, tiles_m, 1u << msd_bits, P, bucket_start, tile_base, c->occ_bits, c->occ_rank,
+           (uint32_t)rem, c->g.cells, c->n_vox, bucket_rank0);
+    CU(cudaMemcpyAsync(c->total_host, tile_base + 256, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += 8;
+    const uint32_t n_tiles = c->total_host[0], max_bucket_vox = c->total_host[1];
+    int kbits = 0;
+    while ((1ull << kbits) < max_bucket_vox) kbits++;
+    const int lp = (kbits + 7) / 8, per = lp ? (kbits + lp - 1) / lp : 0;
     if (lp > 0) {
-        LAUNCH(c, k_sort_bucket_tiles, 1, 256, (const uint32_t*)hist, tiles_m, 1u << msd_bits, P, bucket_start, tile_base);
-        uint32_t n_tiles = 0;
-        if ((rc = read_total(c, tile_base + 256, &n_tiles))) return rc;
-        LAUNCH(c, k_sort_tile_table, div_up(std::max<uint32_t>(n_tiles, 1), kBlock), kBlock, (const uint32_t*)bucket_start, (const uint32_t*)tile_base, tab);
+        LAUNCH(c, k_sort_tile_table, div_up(std::max<uint32_t>(n_tiles, 1), kBlock), kBlock, (const uint32_t*)bucket_start, (const uint32_t*)tile_base,
+               (const uint32_t*)bucket_rank0, tab);
         for (int p = 0; p < lp; p++) {
             SortSrc src{};
             src.keys = kin; src.vals = vin; src.tab = tab; src.n_tiles_dev = tile_base + 256;
-            const uint32_t shift = (uint32_t)(p * per), mask = (1u << per) - 1;   // a last digit reaching into the top digit is constant inside a bucket
+            const uint32_t shift = (uint32_t)(p * per), mask = (1u << per) - 1;
             LAUNCH(c, k_sort_hist<false>, n_tiles, kBlock, src, shift, mask, hist);
             if ((rc = scan_u32(c, hist, hist, (uint64_t)256 * n_tiles, nullptr))) return rc;
             LAUNCH(c, k_sort_scatter<false>, n_tiles, kBlock, src, shift, mask, hist, kout, vout);
@@ -482,9 +491,8 @@ int prepare_sorted(pcf_ctx* c) {
             vout = (vin == (uint32_t*)c->valsA.p) ? (uint32_t*)c->valsB.p : (uint32_t*)c->valsA.p;
         }
     }
-    LAUNCH(c, k_gather_points, div_up(P, kBlock), kBlock, c->log, vin, (uint64_t)P, (float4*)c->sorted.p);
-    LAUNCH(c, k_segment_heads, div_up(P, kBlock), kBlock, kin, (uint64_t)P, c->occ_bits, c->occ_rank, (uint32_t*)c->uv_cell.p,
-           (uint32_t*)c->uv_off.p, c->n_vox);
+    LAUNCH(c, k_gather_points, div_up(P, kBlock), kBlock, c->log, kin, vin, (uint64_t)P, (float4*)c->sorted.p, (uint32_t*)c->uv_cell.p,
+           (uint32_t*)c->uv_off.p);
     CU(cudaGetLastError());
     c->sorted_valid = true;
     return PCF_OK;
