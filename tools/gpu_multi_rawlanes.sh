@@ -1,4 +1,4 @@
-# usage: bash tools/gpu_multi3.sh <N> <tag>   e2e A/B of the raw lanes at N GPUs (no C3 leg)
+# usage: bash tools/gpu_multi_rawlanes.sh <N> <tag>   e2e A/B of the raw lanes at N GPUs (no C3 leg)
 set -x
 cd $GRAFT_REPO_ROOT
 N=${1:-8}; tag=${2:-r}
