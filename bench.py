@@ -173,12 +173,12 @@ def cpu_baseline_run(frames, poses, grid, process=True):
 
 def run_reference(args):
     """Every executed step integrates ALL 200 frames (same work as one step of the B200 arm).  One full pass costs 10-25 s of
-    CPU, so the arm executes as many of the requested W + K passes as fit PCF_REF_BUDGET_S (default 240 s; at least one timed
+    CPU, so the arm executes as many of the requested W + K passes as fit PCF_REF_BUDGET_S (default 150 s; at least one timed
     pass, at most one warm-up pass) and reports their mean: fewer repeats, never fewer frames."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    budget = float(os.environ.get("PCF_REF_BUDGET_S", "240"))
+    budget = float(os.environ.get("PCF_REF_BUDGET_S", "150"))
     t_start = time.perf_counter()
     scene, first = make_scene()
     frames, poses = gen_frames(scene, first, N_FRAMES)

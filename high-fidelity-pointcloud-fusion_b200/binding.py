@@ -47,7 +47,7 @@ class _Stats(C.Structure):
 ABI_SYMBOLS = [
     "pcf_default_config", "pcf_create", "pcf_destroy", "pcf_last_error", "pcf_dims", "pcf_start", "pcf_stop", "pcf_reset",
     "pcf_push_frame", "pcf_push_pointcloud2", "pcf_add_points", "pcf_submit_frame", "pcf_submit_pointcloud2", "pcf_drain", "pcf_stage_frame", "pcf_staged_count", "pcf_wait_staged", "pcf_host_alloc", "pcf_host_free", "pcf_upload_ticket", "pcf_wait_upload", "pcf_push_frames_device", "pcf_sync", "pcf_count_kept", "pcf_update", "pcf_extract", "pcf_process", "pcf_write_result",
-    "pcf_extract_hq", "pcf_clear", "pcf_dump_state", "pcf_get_stats", "pcf_reset_stats", "pcf_last_timings", "pcf_stream",
+    "pcf_extract_hq", "pcf_clear", "pcf_dump_state", "pcf_reserve_process", "pcf_get_stats", "pcf_reset_stats", "pcf_last_timings", "pcf_stream",
     "pcf_grid_buffer", "pcf_viewpoint_table", "pcf_log_compact", "pcf_log_replace", "pcf_set_slab", "pcf_plane_counts", "pcf_plane_point_counts", "pcf_exchange_counts", "pcf_exchange_scatter", "pcf_exchange_hist", "pcf_exchange_plan", "pcf_exchange_scatter_async", "pcf_round_export", "pcf_round_install", "pcf_update_local", "pcf_update_commit", "pcf_recv_buffer", "pcf_ipc_export", "pcf_ipc_open",
     "pcf_ipc_close_all", "pcf_install_records", "pcf_get_viewpoints", "pcf_set_viewpoints", "pcf_enable_peer_access", "pcf_kat_transform_voxel",
     "pcf_kat_normal", "pcf_kat_score", "pcf_kat_format_float", "pcf_kat_clip_pack", "pcf_kat_div",
@@ -97,6 +97,7 @@ def load_library():
     lib.pcf_process.argtypes = [vp, C.c_char_p, C.c_char_p]
     lib.pcf_write_result.argtypes = [C.POINTER(_Result), C.c_char_p, C.c_char_p]
     lib.pcf_dump_state.argtypes = [vp, C.POINTER(_State)]
+    lib.pcf_reserve_process.argtypes = [vp, C.c_uint64, C.c_uint64]
     lib.pcf_get_stats.argtypes = [vp, C.POINTER(_Stats)]
     lib.pcf_last_timings.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.pcf_stream.argtypes = [vp]
@@ -335,6 +336,10 @@ class Fusion:
 
     def clear(self):
         self._ck(self.lib.pcf_clear(self.h))
+
+    def reserve_process(self, max_points, max_voxels):
+        """Pre-size the process() scratch (first-call allocations)."""
+        self._ck(self.lib.pcf_reserve_process(self.h, int(max_points), int(max_voxels)))
 
     def state(self) -> State:
         s = _State()

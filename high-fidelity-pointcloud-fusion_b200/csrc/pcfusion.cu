@@ -1299,6 +1299,33 @@ int pcf_process(pcf_ctx* c, const char* cloud_path, const char* meta_path) {
     return pcf_clear(c);                  // node.cpp:438
 }
 
+// Pre-size the scratch of pcf_update / pcf_extract for up to `max_points` kept points and `max_voxels` occupied voxels, so that
+// the first process() of a scan does not pay for cudaMalloc (a live node calls process() once per scan: 50-500 ms of
+// allocation on the first call otherwise).  Buffers still grow on demand beyond these sizes.
+int pcf_reserve_process(pcf_ctx* c, uint64_t max_points, uint64_t max_voxels) {
+    if (!c) return PCF_ERR_INVALID;
+    ENTER(c);
+    if (max_points >= 0xFFFFFFFFull || max_voxels >= 0xFFFFFFFFull) return fail(c, PCF_ERR_INVALID, "pcf_reserve_process: sizes must fit 32 bits");
+    const size_t P = (size_t)max_points, V = (size_t)max_voxels;
+    const size_t tiles = P / kChunk + 257, chunks = std::max<size_t>(c->cap_chunks, P / 64 + 1);
+    struct { DevBuf* b; size_t bytes; } want[] = {
+        {&c->keysA, P * 4}, {&c->keysB, P * 4}, {&c->valsA, P * 4}, {&c->valsB, P * 4}, {&c->sorted, P * sizeof(float4)},
+        {&c->hist, 256 * std::max(tiles, chunks / kWarps + 1) * 4}, {&c->sort_tab, tiles * sizeof(SortTile) + (257 + 258 + 257) * 4},
+        {&c->tmpA, (size_t)c->n_words * 4}, {&c->tmpB, std::max((size_t)c->n_words, chunks) * 4}, {&c->tmpC, V * 16}, {&c->tmpD, V * 8},
+        {&c->cand, V * 4}, {&c->upd_cell, V * 4}, {&c->upd_nrm, V * 16}, {&c->uv_off, (V + 1) * 4}, {&c->uv_cell, (V + 1) * 4}, {&c->nidx, (V + 1) * 4},
+        {&c->n_cell, V * 4}, {&c->n_nrm, V * 16}, {&c->n_mark, V * 4}, {&c->sc_a, V * 16}, {&c->sc_b, V * 16}, {&c->sc_c, V * 4},
+        {&c->sc_keys, V * 4}, {&c->sc_ids, V * 4}, {&c->sc_okeys, V * 4}, {&c->sc_order, V * 4}, {&c->sc_tab, (V / kChunk + 1) * sizeof(SortTile) + 16},
+        {&c->flags, V * 4}, {&c->slots, V * 4}, {&c->res_dev, V * 64 + 8 * 256}, {&c->scan1, (std::max((size_t)c->n_words, P) / kChunk + 1) * 256 * 4},
+    };
+    for (auto& w : want) {
+        const bool keep = w.b == &c->n_cell || w.b == &c->n_nrm || w.b == &c->n_mark;     // these hold state across calls
+        int rc = reserve(c, *w.b, w.bytes, keep);
+        if (rc) return rc;
+    }
+    int rc = ensure_pinned(c, &c->res_host, &c->res_host_cap, V * 64 + 8 * 256);
+    return rc;
+}
+
 int pcf_dump_state(pcf_ctx* c, pcf_state* out) {
     if (!c || !out) return PCF_ERR_INVALID;
     memset(out, 0, sizeof *out);

@@ -22,6 +22,8 @@ PointcloudFusion::PointcloudFusion(const Params& p) : prm_(p) {
         ctx_ = nullptr;
         return;
     }
+    // a scan of known size: pre-size the process() scratch so that the first getFusedCloud() does not pay for device allocations
+    if (p.log_capacity_hint) pcf_reserve_process(ctx_, p.log_capacity_hint, p.log_capacity_hint / 8 + 1024);
     slots_.resize(p.staging_slots ? p.staging_slots : 1);        // start_ is false until start(), like node.cpp:135
 }
 

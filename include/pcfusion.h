@@ -195,6 +195,9 @@ int pcf_write_result(const pcf_result* res, const char* cloud_path, const char* 
 int pcf_extract_hq(pcf_ctx* ctx, double threshold, pcf_result* out);
 int pcf_clear(pcf_ctx* ctx);    /* clearVoxels() + work lists, OG.hpp:167-183 (D5: full reset) */
 
+/* Optional: pre-size the scratch of pcf_update / pcf_extract for up to max_points kept points and max_voxels occupied voxels,
+ * so that the first process() of a scan does not pay for device allocations (everything still grows on demand). */
+int pcf_reserve_process(pcf_ctx* ctx, uint64_t max_points, uint64_t max_voxels);
 int pcf_dump_state(pcf_ctx* ctx, pcf_state* out);
 int pcf_get_stats(pcf_ctx* ctx, pcf_stats* out);
 int pcf_reset_stats(pcf_ctx* ctx);

@@ -182,3 +182,20 @@ def test_shared_reciprocal_division_is_the_ieee_division(pcf, small):
         m, bad = f.kat_div(x, c)
         assert m == 0, f"rep {rep}: {m} quotients differ, e.g. x={x[bad]!r} c={c[bad]!r}"
     f.close()
+
+
+def test_reserve_process_presizes_scratch_without_changing_results(pcf, small):
+    """pcf_reserve_process: the first update / extract after it runs on pre-sized buffers (a live node's first process());
+    results are the same bytes, and the first extraction is not slower than a warm one by the allocation cost."""
+    g = small.grid
+    frames = [small.frame(i) for i in range(small.n_frames)]
+    a, b = pcf.Fusion(g.box, g.res), pcf.Fusion(g.box, g.res)
+    b.reserve_process(small.n_frames * small.points_per_frame, 200_000)
+    for f in (a, b):
+        for i, (pts, T) in enumerate(frames):
+            f.push_frame(pts, T, i)
+        f.update()
+    ra, rb = a.extract(), b.extract()
+    assert_same(rb, ra, RESULT_FIELDS, "reserve_process: ")
+    assert_same(b.state(), a.state(), STATE_FIELDS, "reserve_process state: ")
+    a.close(); b.close()
