@@ -146,16 +146,17 @@ def test_scoring_variants_are_bit_identical(pcf, oracle, small):
     want = og.download()
     assert len(want) > 20000
     try:
-        for unr, bal, coop in [(1, 0, 0), (1, 1, 0), (2, 1, 0), (4, 1, 0), (4, 0, 0), (1, 1, 1), (1, 0, 1)]:
+        for unr, bal, coop, slots in [(1, 0, 0, 16), (1, 1, 0, 16), (2, 1, 0, 16), (4, 1, 0, 16), (4, 0, 0, 16), (1, 1, 1, 16), (1, 0, 1, 16), (1, 1, 1, 8)]:
             os.environ["PCF_SCORE_UNR"], os.environ["PCF_SCORE_BALANCE"], os.environ["PCF_SCORE_COOP"] = str(unr), str(bal), str(coop)
+            os.environ["PCF_COOP_SLOTS"] = str(slots)
             f = pcf.Fusion(g.box, g.res)
             for i, (pts, T) in enumerate(frames):
                 f.push_frame(pts, T, i)
             f.update()
-            assert_result_parity(f.extract(), want, f"k_score unroll={unr} balance={bal} coop={coop}: ")
+            assert_result_parity(f.extract(), want, f"k_score unroll={unr} balance={bal} coop={coop} slots={slots}: ")
             f.close()
     finally:
-        for k in ("PCF_SCORE_UNR", "PCF_SCORE_BALANCE", "PCF_SCORE_COOP"):
+        for k in ("PCF_SCORE_UNR", "PCF_SCORE_BALANCE", "PCF_SCORE_COOP", "PCF_COOP_SLOTS"):
             os.environ.pop(k, None)
 
 

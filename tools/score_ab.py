@@ -16,7 +16,7 @@ ref = None
 
 def run(env, trace=False):
     global ref
-    for k in ("PCF_SCORE_UNR", "PCF_SCORE_BALANCE", "PCF_SCORE_COOP", "PCF_TRACE"):
+    for k in ("PCF_SCORE_UNR", "PCF_SCORE_BALANCE", "PCF_SCORE_COOP", "PCF_COOP_SLOTS", "PCF_TRACE"):
         os.environ.pop(k, None)
     os.environ.update(env)
     fus = pcf.Fusion(g.box, g.res, log_capacity_hint=200 * npf)
@@ -38,7 +38,7 @@ def run(env, trace=False):
     return dict(env=env, same_result=best_same, **best)
 
 
-for coop, bal in ((0, 0), (0, 1), (1, 0), (1, 1)):
-    print(json.dumps(run({"PCF_SCORE_COOP": str(coop), "PCF_SCORE_BALANCE": str(bal)})), flush=True)
+for coop, bal, slots in ((0, 1, 16), (1, 0, 16), (1, 1, 16), (1, 1, 8), (1, 1, 16), (1, 1, 8)):
+    print(json.dumps(run({"PCF_SCORE_COOP": str(coop), "PCF_SCORE_BALANCE": str(bal), "PCF_COOP_SLOTS": str(slots)})), flush=True)
 print("---- trace of the default configuration ----", file=sys.stderr, flush=True)
 print(json.dumps(run({"PCF_TRACE": "1"}, trace=True)), flush=True)
