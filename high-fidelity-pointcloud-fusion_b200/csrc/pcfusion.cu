@@ -107,7 +107,7 @@ struct pcf_ctx {
         sc_a, sc_b, sc_c, flags, slots, cand, res_dev, total_dev, sc_keys, sc_ids, sc_order, sc_okeys, sc_tab;
     int score_unroll = 1;                 // PCF_SCORE_UNR: cylinder tests evaluated back to back in k_score (1, 2 or 4; measured: no gain)
     bool score_balance = true;            // PCF_SCORE_BALANCE=0 keeps the x-major voxel -> lane assignment
-    int coop_slots = 8;                   // PCF_COOP_SLOTS: 4, 8 or 16 points per voxel and round in k_score_coop (measured: 8 is best)
+    int coop_slots = 8;                   // PCF_COOP_SLOTS: 8 or 16 points per voxel and round in k_score_coop
     int score_coop = -1;                  // PCF_SCORE_COOP: 1 always / 0 never use k_score_coop on canonical schedules (-1: by point density)
     uint32_t* total_host = nullptr;       // pinned, 4 words
     // host results (pinned)
@@ -556,8 +556,7 @@ int run_scoring(pcf_ctx* c) {
     const bool coop = simple && c->score_coop != 0 && (c->score_coop > 0 || c->n_points >= 8ull * std::max<uint32_t>(c->n_vox, 1u));
 #define COOP_ARGS order, (const uint32_t*)c->n_cell.p, (const float4*)c->n_nrm.p, nn, c->g, c->occ_bits, c->occ_rank, (const uint32_t*)c->uv_off.p, \
                   (const float4*)c->sorted.p, so, (uint32_t)c->n_points, (const uint32_t*)c->uv_cell.p, fault, cell_lo, cell_hi
-    if (coop && c->coop_slots == 4) LAUNCH(c, k_score_coop<4>, div_up(nn, kCoopWarps * 32), kCoopWarps * 32, COOP_ARGS);
-    else if (coop && c->coop_slots == 8) LAUNCH(c, k_score_coop<8>, div_up(nn, kCoopWarps * 32), kCoopWarps * 32, COOP_ARGS);
+    if (coop && c->coop_slots == 8) LAUNCH(c, k_score_coop<8>, div_up(nn, kCoopWarps * 32), kCoopWarps * 32, COOP_ARGS);
     else if (coop) LAUNCH(c, k_score_coop<16>, div_up(nn, kCoopWarps * 32), kCoopWarps * 32, COOP_ARGS);
 #undef COOP_ARGS
     else if (!simple) LAUNCH(c, (k_score<false, 1>), div_up(nn, 128), 128, SCORE_ARGS);
@@ -780,7 +779,7 @@ int pcf_create(const pcf_config* cfg, pcf_ctx** out) {
         const char* bl = getenv("PCF_SCORE_BALANCE");
         if (bl) c->score_balance = atoi(bl) != 0;
         const char* cs = getenv("PCF_COOP_SLOTS");
-        if (cs && (atoi(cs) == 4 || atoi(cs) == 8 || atoi(cs) == 16)) c->coop_slots = atoi(cs);
+        if (cs && (atoi(cs) == 8 || atoi(cs) == 16)) c->coop_slots = atoi(cs);
         const char* co = getenv("PCF_SCORE_COOP");
         if (co) c->score_coop = atoi(co) != 0 ? 1 : 0;
     }

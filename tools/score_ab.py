@@ -38,7 +38,7 @@ def run(env, trace=False):
     return dict(env=env, same_result=best_same, **best)
 
 
-for coop, bal, slots in ((1, 1, 16), (1, 1, 8), (1, 1, 4), (1, 1, 8), (1, 1, 4)):
+for coop, bal, slots in ((0, 0, 16), (0, 1, 16), (1, 0, 8), (1, 1, 16), (1, 1, 8)):
     print(json.dumps(run({"PCF_SCORE_COOP": str(coop), "PCF_SCORE_BALANCE": str(bal), "PCF_COOP_SLOTS": str(slots)})), flush=True)
 print("---- trace of the default configuration ----", file=sys.stderr, flush=True)
 print(json.dumps(run({"PCF_TRACE": "1"}, trace=True)), flush=True)
