@@ -953,10 +953,15 @@ static int ensure_stager(pcf_ctx* c) {
         return push_host_cloud_impl(c, xyz, (size_t)n_staged * 12, 0, n_staged, 3, nullptr, pose, nullptr, frame_idx, n_offered, c->slot_ev[s]);
     };
     // raw lanes: measured harmful where the packers saturate the host's memory bandwidth (16 vCPUs, 12 packers: 6.0 -> 5.4 G
-    // points/s) and useful where cores are scarce (8 GPUs on 32 vCPUs, 3 packers per GPU: the link would idle behind them).
-    // Auto: none with 8 or more packers, else 8 (every lane holds one cloud in flight; a lane waits for its own copy, so
-    // the link is never oversubscribed).
-    int raw_lanes = c->cfg.stage_raw_lanes == 0 ? (threads >= 8 ? 0 : 8) : std::max(c->cfg.stage_raw_lanes, 0);
+    // points/s) and useful where cores are scarce (8 GPUs on 32 vCPUs: 3 packers 8.5 G, 3 packers + 8 lanes 9.9 G, 1 packer +
+    // 12 lanes 11.6 G points/s -- there the link, not the packers, should carry the clouds).  Auto: none with 8 or more
+    // packers, else "upload mode" = 1 packer + 12 lanes (every lane holds one cloud in flight and waits for its own copy, so
+    // the link is never oversubscribed; clouds that are not pinned are packed by the lanes as well).
+    int raw_lanes = std::max(c->cfg.stage_raw_lanes, 0);
+    if (c->cfg.stage_raw_lanes == 0 && !getenv("PCF_RAW_LANES")) {
+        raw_lanes = threads >= 8 ? 0 : 12;
+        if (threads < 8 && !getenv("PCF_STAGE_THREADS")) threads = 1;
+    }
     if (const char* e = getenv("PCF_RAW_LANES")) raw_lanes = std::max(atoi(e), 0);
     h.raw_ok = [](const StageJob& j) {
         if (j.x_offset != 0 || (j.point_step != 16 && j.point_step != 12) || ((uintptr_t)j.data & 15u)) return false;

@@ -60,7 +60,8 @@ typedef struct {
     int32_t stage_raw_lanes;     /* extra threads that upload pinned float4 / xyz clouds UNSTAGED while clouds pile up behind the
                                     packers, using the PCIe time the staged copies leave free.  0 = auto: none when there are 8 or
                                     more packers (they saturate the host's memory bandwidth; raw DMA traffic then costs more than
-                                    it brings), 8 on core-starved hosts; < 0 = none; env PCF_RAW_LANES overrides */
+                                    it brings); with fewer, "upload mode": 1 packer + 12 lanes (core-starved hosts: the link
+                                    carries the clouds).  < 0 = none; env PCF_RAW_LANES overrides */
 } pcf_config;
 
 /* Extraction output, structure of arrays, x-major voxel order = the reference's scan order
