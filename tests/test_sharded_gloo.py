@@ -136,3 +136,62 @@ def test_exchange_v2_routing_world2(tmp_path):
         assert np.array_equal(outs[d]["recv"].view(np.uint32), want.view(np.uint32))
     loads = [int(((x1 >= b[d]) & (x1 < b[d + 1])).sum()) for d in range(world)]
     assert sum(loads) == len(log1) and min(loads) > 0.3 * len(log1)
+
+
+# ---- interleaved schedules across ranks (replicated state): the variable-size gathers over gloo, world_size 2 ------------
+def _worker_rounds(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sh, _, _, _, _ = _rank_state(rank, world)
+    import golden_util as G
+    import oracle as O
+    fx = G.load("sphere_5mm")
+    nf, every = len(fx.frames), 2
+    merged_rounds, vp_table = [], torch.zeros((16, 4), dtype=torch.float32)
+    for start in range(0, nf, every):
+        stop = min(start + every, nf)
+        lo, hi = sh.frame_block(stop - start, rank, world)          # this rank's frames of the round
+        recs = []
+        for i in range(start + lo, start + hi):
+            pts, T = fx.frames[i], fx.poses[i]
+            z = pts[:, 2].astype(np.float64)
+            w = O.kat_transform(T, pts[(z < fx.clip[1]) & (z > fx.clip[0])])
+            r = np.zeros((len(w), 4), np.float32)
+            r[:, :3] = w
+            r[:, 3] = np.uint32(i).view(np.float32)                 # (x, y, z, frame_idx): what pcf_round_export emits
+            recs.append(r)
+            vp_table[i] = torch.tensor([np.float32(T[0, 3]), np.float32(T[1, 3]), np.float32(T[2, 3]), 1.0])
+        mine = torch.from_numpy(np.concatenate(recs) if recs else np.zeros((0, 4), np.float32))
+        merged_rounds.append(sh._gather_var(mine, None).numpy())   # rank order == frame order == arrival order
+        dist.all_reduce(vp_table[start:stop])                       # rows of this round only
+    np.savez(os.path.join(out_dir, f"il{rank}.npz"), merged=np.concatenate(merged_rounds), vps=vp_table.numpy())
+    dist.destroy_process_group()
+
+
+def test_interleaved_round_gathers_world2(tmp_path):
+    """Every rank must end up with the same merged record stream, equal to the single-rank arrival order, and with every
+    frame's viewpoint row exactly once (rows are summed per round, never twice)."""
+    world = 2
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_worker_rounds, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import golden_util as G
+    import oracle as O
+    fx = G.load("sphere_5mm")
+    want, vps = [], np.zeros((16, 4), np.float32)
+    for i in range(len(fx.frames)):
+        pts, T = fx.frames[i], fx.poses[i]
+        z = pts[:, 2].astype(np.float64)
+        w = O.kat_transform(T, pts[(z < fx.clip[1]) & (z > fx.clip[0])])
+        r = np.zeros((len(w), 4), np.float32)
+        r[:, :3] = w
+        r[:, 3] = np.uint32(i).view(np.float32)
+        want.append(r)
+        vps[i] = [np.float32(T[0, 3]), np.float32(T[1, 3]), np.float32(T[2, 3]), 1.0]
+    want = np.concatenate(want)
+    outs = [np.load(tmp_path / f"il{r}.npz") for r in range(world)]
+    for o in outs:
+        assert np.array_equal(o["merged"].view(np.uint32), want.view(np.uint32))
+        assert np.array_equal(o["vps"], vps)
