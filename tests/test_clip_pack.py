@@ -56,3 +56,17 @@ def test_clip_pack_all_implementations_agree_with_the_definition(point_step, x_o
         got[isa] = out
     for isa in (1, 2, -1, "2-unaligned"):
         assert np.array_equal(got[isa].view(np.uint32), got[0].view(np.uint32))
+
+
+def test_staging_pool_ordering_contract_cpu():
+    """tests/cpp/stager_check.cpp: the pool (csrc/pcf_stager.hpp) with fake GPU hooks -- hand-over strictly in submission order
+    for every mix of packers and raw lanes, each cloud exactly once with its own packed payload, drop_queued / drain semantics."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-s", "-C", os.path.join(root, "high-fidelity-pointcloud-fusion_b200"), "all"], check=True)
+    subprocess.run(["make", "-s", "-C", os.path.join(root, "host"), "all"], check=True)
+    for rep in range(3):
+        r = subprocess.run([os.path.join(root, "tests", "_build", "stager_check")], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert r.stdout.count("OK ") == 7
