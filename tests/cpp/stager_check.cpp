@@ -39,6 +39,7 @@ static int run(int threads, int raw_lanes, int n_clouds, bool pinned, int drop_a
     h.raw_ok = [pinned](const StageJob& j) { return pinned && j.point_step == 16; };
     h.push = [&](int, const float* xyz, uint32_t n_staged, uint32_t n_offered, const double* pose, uint32_t frame_idx) {
         order.push_back(frame_idx);
+        if (drop_after >= 0) std::this_thread::sleep_for(std::chrono::microseconds(100));   // a slow GPU hand-over: clouds pile up in the queue
         const Cloud& c = clouds[frame_idx];
         if (pose[5] != (double)frame_idx || n_offered != c.xyzw.size() / 4 || n_staged % 4) bad++;
         uint32_t k = 0;                               // the packed payload must be this cloud's kept points, in order
