@@ -163,6 +163,13 @@ def test_c4_hires_half_millimetre_interleaved_bit_exact_vs_oracle(pcf, oracle):
 def test_c5_ten_million_voxels_full_grid_bit_exact_vs_oracle(pcf, oracle):
     """C5's shape on the full 1 m @ 1 mm grid: 10 one-voxel-thick wavy sheets of 1000 x 1000 voxels (1e7 occupied voxels,
     1-4 points each) through pcf_add_points (OccupancyGrid::addPoints semantics), update + extraction vs the oracle."""
+    avail_gb = 0.0
+    try:
+        avail_gb = [int(l.split()[1]) for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0] / 1e6
+    except Exception:
+        pass
+    if avail_gb < 48:      # the oracle keeps the reference's per-voxel objects and leaked holders: ~18 GB of host memory at this size
+        pytest.skip(f"host has {avail_gb:.0f} GB available; the CPU oracle needs ~18 GB for 1.1e7 voxels (48 GB required for head-room)")
     g, sheets = _synth(pcf).wavy_sheets_world(n_sheets=10, n_side=1000)
     fus = pcf.Fusion(g.box, g.res, log_capacity_hint=sum(len(p) for p, _ in sheets))
     og = oracle.OracleGrid(g.box, g.res)
